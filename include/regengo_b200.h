@@ -1,0 +1,171 @@
+/*
+ * regengo_b200 -- C ABI of the B200 matching path.
+ *
+ * The reference (KromDaniel/regengo) has no FFI: its hot path is the method set that
+ * `regengo.Compile` GENERATES per pattern (internal/compiler/compiler.go:204-367).  A drop-in
+ * replaces the *bodies* of those generated methods with calls into this library (INTEGRATION.md
+ * shows the cgo stub).  Every entry point below names the generated method it stands in for.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the library never owns caller memory;
+ *   - every function returns >= 0 on success and a negative RGX_E* code on failure; a message
+ *     can be fetched with rgx_last_error() (thread-local);
+ *   - there is NO CPU matching path: without a usable CUDA device every compute entry point
+ *     returns RGX_ECUDA.  Only the compile/inspect functions work without a GPU;
+ *   - a `rgx_program` is immutable after creation and may be shared between threads; a `rgx_ctx`
+ *     owns one CUDA stream plus scratch and must not be used from two threads at once
+ *     (mirrors the reference's stateless receivers + sync.Pool scratch, pool.go:11-169).
+ *
+ * Result layout ("offset records")
+ *   One match = 2*(k+1) int64 byte offsets into the caller's input, group 0 first
+ *   (k = number of capture groups): [start0,end0,start1,end1,...].  A group the reference
+ *   would leave nil is (-1,-1).  This is the flat form of the generated `<Name>BytesResult`
+ *   struct of []byte slices (captures.go:83-118): field i == input[start_i:end_i].
+ */
+#ifndef REGENGO_B200_H
+#define REGENGO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGX_OK 0
+#define RGX_EINVAL (-1)      /* bad argument */
+#define RGX_EPATTERN (-2)    /* pattern does not parse / unsupported construct */
+#define RGX_EUNSUPPORTED (-3)/* method not generated for this pattern (e.g. Find* without captures) */
+#define RGX_ECUDA (-4)       /* no device / CUDA failure */
+#define RGX_ENOMEM (-5)
+#define RGX_EBUFFER_TOO_SMALL (-6) /* stream.ErrBufferTooSmall (stream/stream.go:96-101) */
+#define RGX_ECAPACITY (-7)   /* caller output buffer too small; see the function's doc */
+
+typedef struct rgx_program rgx_program;
+typedef struct rgx_ctx rgx_ctx;
+
+/* regengo.Options fields that change matching semantics (regengo.go:13-65). */
+typedef struct rgx_options {
+  int32_t force_thompson;  /* Options.ForceThompson */
+  int32_t force_tnfa;      /* Options.ForceTNFA     */
+  int32_t force_tdfa;      /* Options.ForceTDFA     */
+  int32_t tdfa_threshold;  /* Options.TDFAThreshold, 0 => 500 */
+} rgx_options;
+
+/* What the generator decided for a pattern (compiler.go:93-184). */
+typedef struct rgx_info {
+  int32_t n_inst;          /* len(prog.Inst) */
+  int32_t num_cap;         /* prog.NumCap = 2*(k+1) */
+  int32_t n_groups;        /* k */
+  int32_t match_engine;    /* 0 backtracking, 1 Thompson bitset */
+  int32_t find_engine;     /* 0 none (no captures => no Find* methods), 1 backtracking, 2 TDFA */
+  int32_t match_memo;      /* visited bit-vector in Match*  */
+  int32_t find_memo;       /* visited bit-vector in Find* ("TNFA") */
+  int32_t per_capture_ckpt;/* per-capture (1) or array (0) checkpointing */
+  int32_t anchored;
+  int32_t min_match_len;   /* <Name>MinMatchLen */
+  int32_t max_match_len;   /* <Name>MaxMatchLen, -1 unbounded */
+  int32_t default_max_leftover; /* DefaultMaxLeftover() (streaming.go:25-46) */
+  int32_t min_buffer;      /* cfg.Validate(minBuffer) (streaming.go:56-62) */
+  int32_t tdfa_states;     /* 0 unless find_engine == 2 */
+  int32_t tdfa_tags;
+  int32_t reserved[5];
+} rgx_info;
+
+/* ---- generation time: stands in for regengo.Compile (regengo.go:86-156) ------------------ */
+
+/* Parse(Perl) -> Simplify -> Compile -> analysis -> engine selection -> tables. Host only. */
+int rgx_compile(const char* pattern, const rgx_options* opts /* may be NULL */, rgx_program** out);
+void rgx_program_free(rgx_program* p);
+int rgx_program_info(const rgx_program* p, rgx_info* out);
+/* JSON dump of the program (Prog listing, masks, TDFA tables); the string lives as long as p. */
+const char* rgx_program_json(const rgx_program* p);
+/* Name of capture group i (1..k), "" if unnamed; NULL if out of range. */
+const char* rgx_program_group_name(const rgx_program* p, int32_t i);
+
+/* The packed per-pattern "program blob" a retargeted Go generator would embed in place of the
+ * goto-machine.  rgx_program_blob: returns the blob size in bytes; copies it when cap suffices. */
+int64_t rgx_program_blob(const rgx_program* p, void* buf, size_t cap);
+int rgx_load(const void* blob, size_t n, rgx_program** out);
+
+const char* rgx_last_error(void);
+const char* rgx_version(void);
+
+/* ---- device context ---------------------------------------------------------------------- */
+
+int rgx_ctx_create(int32_t device, rgx_ctx** out);
+void rgx_ctx_destroy(rgx_ctx* c);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
+int64_t rgx_ctx_launches(const rgx_ctx* c);
+/* The context's CUDA stream as an opaque cudaStream_t, for event timing on the launching stream. */
+void* rgx_ctx_stream(const rgx_ctx* c);
+int rgx_ctx_sync(rgx_ctx* c);
+
+/* ---- MatchBytes: func (T) MatchBytes(input []byte) bool  (compiler.go:304-307, 740-871;
+ *      Thompson variant thompson.go:69-131).  Batch extension: input i = bytes[offs[i]:offs[i+1]],
+ *      out[i] = 0/1.  Host pointers.                                                            */
+int rgx_match_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const uint64_t* offs,
+                    uint64_t n, uint8_t* out);
+/* Same with DEVICE pointers (inputs already resident in HBM); asynchronous on the ctx stream. */
+int rgx_match_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes,
+                        const uint64_t* d_offs, uint64_t n, uint8_t* d_out);
+
+/* ---- FindBytes: func (T) FindBytes(input []byte) (*TBytesResult, bool)  (find.go:41-67,
+ *      469-591; TDFA compiler.go:505-534 + tdfa.go:831-1052).  Batch extension: found[i] = 0/1,
+ *      out_offsets[i*num_cap ..] = offset record relative to input i (undefined if !found).     */
+int rgx_find_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const uint64_t* offs,
+                   uint64_t n, uint8_t* found, int64_t* out_offsets);
+int rgx_find_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes,
+                       const uint64_t* d_offs, uint64_t n, uint8_t* d_found, int64_t* d_out_offsets);
+
+/* ---- FindAllBytes: func (T) FindAllBytes(input []byte, n int) []*TBytesResult
+ *      (backtracking find.go:100-316; TDFA compiler.go:602-655).  n_limit < 0: all; 0: none.
+ *      Writes up to cap_matches offset records; returns the number of matches the reference
+ *      would return (if > cap_matches only the first cap_matches were written).
+ *      The TDFA variant reproduces the reference's stride rule, so a match can repeat
+ *      (SURVEY.md Q2); repeats are written out as individual records here.                      */
+int64_t rgx_find_all(rgx_ctx* c, const rgx_program* p, const uint8_t* buf, uint64_t len,
+                     int64_t n_limit, int64_t* out_offsets, uint64_t cap_matches);
+
+/* Device-resident form.  Results stay on the device in run-length form: record j is the offset
+ * record of one distinct match and d_reps[j] how many consecutive times the reference returns
+ * it (always 1 for the backtracking engine).  *n_records = distinct records written (<= cap),
+ * return value = sum of reps = len(FindAllBytes(...)).  If the distinct records exceed
+ * cap_records, returns RGX_ECAPACITY and sets *n_records to the number required.             */
+int64_t rgx_find_all_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t len,
+                         int64_t n_limit, int64_t* d_out_offsets, uint32_t* d_reps,
+                         uint64_t cap_records, uint64_t* n_records);
+
+/* ---- FindReader: func (T) FindReader(r io.Reader, cfg stream.Config, onMatch ...) error
+ *      (streaming.go:85-255) for a reader that fills every Read (bytes.Reader semantics) over
+ *      `stream[0:len]`.  buffer_size/max_leftover are stream.Config{BufferSize, MaxLeftover}
+ *      before ApplyDefaults (0 => defaults).  Per match: StreamOffset, ChunkIndex and the offset
+ *      record relative to the chunk buffer.  The callback's early stop is applied by the caller
+ *      (truncate at the first `false`).  Returns the match count (see rgx_find_all for cap).
+ *      first_chunk/n_chunks select a chunk range [first_chunk, first_chunk+n_chunks) so that a
+ *      stream can be sharded over GPUs (n_chunks < 0: to the end).                              */
+int64_t rgx_find_reader(rgx_ctx* c, const rgx_program* p, const uint8_t* stream, uint64_t len,
+                        int64_t buffer_size, int64_t max_leftover, int64_t first_chunk,
+                        int64_t n_chunks, int64_t* out_stream_off, int32_t* out_chunk_idx,
+                        int64_t* out_offsets, uint64_t cap_matches);
+/* Device-resident stream; d_stream points at stream byte `base` (the shard's first byte) and
+ * holds `len` bytes of it; total_len is the length of the whole stream.                         */
+int64_t rgx_find_reader_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_stream,
+                            uint64_t base, uint64_t len, uint64_t total_len, int64_t buffer_size,
+                            int64_t max_leftover, int64_t first_chunk, int64_t n_chunks,
+                            int64_t* d_out_stream_off, int32_t* d_out_chunk_idx,
+                            int64_t* d_out_offsets, uint64_t cap_matches);
+/* stream.Config.Validate + ApplyDefaults (stream/stream.go:96-134) for this pattern. */
+int rgx_stream_config(const rgx_program* p, int64_t buffer_size, int64_t max_leftover,
+                      int64_t* eff_buffer_size, int64_t* eff_max_leftover);
+
+/* ---- device memory helpers (so that a host language without CUDA bindings can stage data) -- */
+int rgx_dev_alloc(rgx_ctx* c, size_t bytes, void** out);
+int rgx_dev_free(rgx_ctx* c, void* p);
+int rgx_dev_upload(rgx_ctx* c, void* d_dst, const void* h_src, size_t bytes);
+int rgx_dev_download(rgx_ctx* c, void* h_dst, const void* d_src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGENGO_B200_H */

@@ -1,0 +1,546 @@
+// Device half of the C ABI (include/regengo_b200.h): contexts, per-device program images and the
+// launch logic of every compute entry point.  There is no CPU matching path in this library: if
+// CUDA is unavailable every function here fails with RGX_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "capi_internal.hpp"
+#include "device_program.cuh"
+#include "engines.cuh"
+#include "kernels_batch.cuh"
+#include "kernels_findall.cuh"
+#include "kernels_stream.cuh"
+
+using namespace rgx;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct rgx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int64_t launches = 0;
+  // grow-only scratch
+  DevBuf stack, cstack, visited, small, in_bytes, in_offs, out_flag, out_rec, out_reps, out_aux;
+  DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase;
+  void* h_small = nullptr;  // pinned, 4 KiB
+  uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
+  uint32_t fa_stack_cap = 256;
+};
+
+namespace {
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+      return RGX_ECUDA;                                                                              \
+    }                                                                                                \
+  } while (0)
+
+int ensure(rgx_ctx* c, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return RGX_OK;
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t want = std::max(bytes, (size_t)256);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); b.p = nullptr; return e == cudaErrorMemoryAllocation ? RGX_ENOMEM : RGX_ECUDA; }
+  b.cap = want;
+  (void)c;
+  return RGX_OK;
+}
+
+void free_buf(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+// small device block: [0] err flags (int), [8..] totals / flags (8-byte slots)
+struct Small {
+  int* err;
+  unsigned long long* slots;  // 16 slots
+};
+Small small_of(rgx_ctx* c) { return Small{(int*)c->small.p, (unsigned long long*)((char*)c->small.p + 64)}; }
+
+int get_image(rgx_ctx* c, const rgx_program* p, const DeviceImage** out) {
+  std::lock_guard<std::mutex> g(p->mu);
+  if ((size_t)c->device >= p->images.size()) p->images.resize(c->device + 1, nullptr);
+  DeviceImage* im = p->images[c->device];
+  if (!im) {
+    im = new DeviceImage();
+    std::vector<uint32_t> words;
+    pack_program(p->prog, words, im->meta);
+    im->in_smem = words.size() * 4 <= SMEM_IMAGE_LIMIT;
+    cudaError_t e = cudaMalloc(&im->d_words, words.size() * 4);
+    if (e != cudaSuccess) { delete im; set_error(std::string("cudaMalloc(image): ") + cudaGetErrorString(e)); return RGX_ECUDA; }
+    e = cudaMemcpy(im->d_words, words.data(), words.size() * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(im->d_words); delete im; set_error(std::string("cudaMemcpy(image): ") + cudaGetErrorString(e)); return RGX_ECUDA; }
+    p->images[c->device] = im;
+  }
+  *out = im;
+  return RGX_OK;
+}
+
+int check_caps(const DeviceImage* im, bool find) {
+  const DevMeta& m = im->meta;
+  if (m.num_cap > MAX_CAPS || (find && m.find_engine == FIND_TDFA && m.t_ntags > MAX_CAPS)) {
+    set_error("pattern has more capture groups than the device engines support (2*(k+1) <= 32)");
+    return RGX_EUNSUPPORTED;
+  }
+  if (m.n_inst > 65535) { set_error("program too large for the device engines"); return RGX_EUNSUPPORTED; }
+  return RGX_OK;
+}
+
+template <class K>
+int occupancy_grid(rgx_ctx* c, K kernel, int block, size_t smem, int* grid) {
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+  if (per_sm < 1) per_sm = 1;
+  *grid = per_sm * c->sm_count;
+  return RGX_OK;
+}
+
+// Size the per-thread backtracking scratch for `threads` machines over inputs of at most max_len
+// bytes.  stack_cap == 0 asks for the provable worst case (one entry per (Alt|Capture, offset)).
+int plan_scratch(rgx_ctx* c, const DevMeta& m, bool find, uint32_t threads, uint64_t max_len, uint32_t stack_cap,
+                 bool visited_for_len, ScratchPlan* sp) {
+  std::memset(sp, 0, sizeof(*sp));
+  sp->stride = threads;
+  const bool needs_bt = (m.flags & F_NEEDS_BT) != 0;
+  const bool per_capture = find && (m.flags & F_PER_CAPTURE);
+  const bool memo = find ? (m.flags & F_FIND_MEMO) != 0 : (m.flags & F_MATCH_MEMO) != 0;
+  const bool bt_engine = find ? m.find_engine == FIND_BT : m.match_engine == MATCH_BT;
+  if (!bt_engine) return RGX_OK;
+  if (needs_bt || per_capture) {
+    uint64_t worst = ((uint64_t)m.n_alt + (per_capture ? (uint64_t)m.n_capinst : 0)) * (max_len + 1) + 4;
+    uint64_t cap = stack_cap ? std::min<uint64_t>(stack_cap, worst) : worst;
+    if (cap > 0x7FFFFFFFull) { set_error("backtracking stack bound too large"); return RGX_ENOMEM; }
+    sp->stack_cap = (uint32_t)cap;
+    int rc = ensure(c, c->stack, (size_t)cap * threads * sizeof(uint2));
+    if (rc) return rc;
+    sp->stack = (uint2*)c->stack.p;
+    if (find && !per_capture) {
+      sp->cstack_cap = (uint32_t)cap;
+      rc = ensure(c, c->cstack, (size_t)cap * m.num_cap * threads * sizeof(int32_t));
+      if (rc) return rc;
+      sp->cstack = (int32_t*)c->cstack.p;
+    }
+  }
+  if (memo && visited_for_len) {
+    uint64_t words = ((uint64_t)m.n_inst * (max_len + 1) + 31) / 32;
+    if (words * threads * 4 > (1ull << 36)) { set_error("memoisation bit-vector too large for this input"); return RGX_ENOMEM; }
+    sp->visited_words = (uint32_t)words;
+    int rc = ensure(c, c->visited, (size_t)words * threads * 4);
+    if (rc) return rc;
+    sp->visited = (uint32_t*)c->visited.p;
+  }
+  return RGX_OK;
+}
+
+int read_small(rgx_ctx* c, size_t bytes) {  // device small block -> pinned host copy, synchronised
+  CU(cudaMemcpyAsync(c->h_small, c->small.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
+}
+
+std::string err_bits(int e) {
+  std::string s;
+  if (e & ERR_STACK) s += " backtrack-stack";
+  if (e & ERR_CSTACK) s += " capture-stack";
+  if (e & ERR_VISITED) s += " visited";
+  if (e & ERR_RANGE) s += " offset-range";
+  if (e & ERR_SLAB) s += " record-slab";
+  return s;
+}
+
+}  // namespace
+
+namespace rgx {
+void release_device_program(rgx_program* p) {
+  for (DeviceImage* im : p->images) {
+    if (!im) continue;
+    if (im->d_words) cudaFree(im->d_words);
+    delete im;
+  }
+  p->images.clear();
+}
+}  // namespace rgx
+
+extern "C" {
+
+int rgx_ctx_create(int32_t device, rgx_ctx** out) {
+  if (!out) { set_error("rgx_ctx_create: null argument"); return RGX_EINVAL; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error(std::string("no CUDA device available (this library has no CPU matching path): ") + cudaGetErrorString(e));
+    return RGX_ECUDA;
+  }
+  if (device < 0 || device >= n) { set_error("rgx_ctx_create: bad device ordinal"); return RGX_EINVAL; }
+  CU(cudaSetDevice(device));
+  auto* c = new rgx_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete c;
+    set_error("regengo_b200 is built for sm_100a only");
+    return RGX_ECUDA;
+  }
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMallocHost(&c->h_small, 4096));
+  int rc = ensure(c, c->small, 4096);
+  if (rc) { delete c; return rc; }
+  CU(cudaMemsetAsync(c->small.p, 0, 4096, c->stream));
+  *out = c;
+  return RGX_OK;
+}
+
+void rgx_ctx_destroy(rgx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->stack, &c->cstack, &c->visited, &c->small, &c->in_bytes, &c->in_offs, &c->out_flag, &c->out_rec,
+                    &c->out_reps, &c->out_aux, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
+                    &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase};
+  for (DevBuf* b : bufs) free_buf(*b);
+  if (c->h_small) cudaFreeHost(c->h_small);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int64_t rgx_ctx_launches(const rgx_ctx* c) { return c ? c->launches : 0; }
+void* rgx_ctx_stream(const rgx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int rgx_ctx_sync(rgx_ctx* c) {
+  if (!c) return RGX_EINVAL;
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
+}
+
+int rgx_dev_alloc(rgx_ctx* c, size_t bytes, void** out) {
+  if (!c || !out) return RGX_EINVAL;
+  CU(cudaSetDevice(c->device));
+  cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return RGX_ENOMEM; }
+  return RGX_OK;
+}
+int rgx_dev_free(rgx_ctx* c, void* p) {
+  if (!c) return RGX_EINVAL;
+  CU(cudaSetDevice(c->device));
+  CU(cudaFree(p));
+  return RGX_OK;
+}
+int rgx_dev_upload(rgx_ctx* c, void* d, const void* h, size_t bytes) {
+  if (!c) return RGX_EINVAL;
+  CU(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
+}
+int rgx_dev_download(rgx_ctx* c, void* h, const void* d, size_t bytes) {
+  if (!c) return RGX_EINVAL;
+  CU(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
+}
+
+// ---- batched MatchBytes / FindBytes -------------------------------------------------------------------
+static int batch_dev(rgx_ctx* c, const rgx_program* p, int what, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t n,
+                     uint8_t* d_flag, int64_t* d_rec) {
+  if (!c || !p) { set_error("null context/program"); return RGX_EINVAL; }
+  if (n == 0) return RGX_OK;
+  CU(cudaSetDevice(c->device));
+  const DeviceImage* im;
+  int rc = get_image(c, p, &im);
+  if (rc) return rc;
+  const DevMeta& m = im->meta;
+  if (what == 1 && m.find_engine == FIND_NONE) {
+    set_error("FindBytes is not generated for a pattern without capture groups (regengo.go:110)");
+    return RGX_EUNSUPPORTED;
+  }
+  rc = check_caps(im, what == 1);
+  if (rc) return rc;
+  Small sm = small_of(c);
+  // longest input (sizes the per-thread scratch)
+  CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
+  max_len_kernel<<<std::max(1, c->sm_count), 256, 0, c->stream>>>(d_offs, n, sm.slots);
+  c->launches++;
+  rc = read_small(c, 256);
+  if (rc) return rc;
+  const uint64_t max_len = *(unsigned long long*)((char*)c->h_small + 64);
+  const size_t smem = im->in_smem ? (size_t)m.image_words * 4 : 0;
+  int grid = 0;
+  if (what == 0) rc = occupancy_grid(c, batch_kernel<0>, 256, smem, &grid);
+  else rc = occupancy_grid(c, batch_kernel<1>, 256, smem, &grid);
+  if (rc) return rc;
+  const uint64_t need_blocks = (n + 255) / 256;
+  if ((uint64_t)grid > need_blocks) grid = (int)need_blocks;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    ScratchPlan sp;
+    const uint32_t cap = attempt == 0 ? (uint32_t)std::min<uint64_t>(2 * max_len + 64, 1u << 20) : 0;
+    rc = plan_scratch(c, m, what == 1, (uint32_t)grid * 256u, max_len, cap, true, &sp);
+    if (rc == RGX_ENOMEM && grid > c->sm_count) { grid = c->sm_count; attempt--; continue; }
+    if (rc) return rc;
+    CU(cudaMemsetAsync(sm.err, 0, sizeof(int), c->stream));
+    if (what == 0)
+      batch_kernel<0><<<grid, 256, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_bytes, d_offs, n, d_flag, d_rec, sp, sm.err);
+    else
+      batch_kernel<1><<<grid, 256, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_bytes, d_offs, n, d_flag, d_rec, sp, sm.err);
+    c->launches++;
+    CU(cudaGetLastError());
+    rc = read_small(c, 64);
+    if (rc) return rc;
+    const int e = *(int*)c->h_small;
+    if (e == 0) return RGX_OK;
+    if (attempt == 1 || !(e & (ERR_STACK | ERR_CSTACK))) {
+      set_error("device engine scratch exhausted:" + err_bits(e));
+      return RGX_ENOMEM;
+    }
+  }
+  return RGX_OK;
+}
+
+int rgx_match_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t n, uint8_t* d_out) {
+  return batch_dev(c, p, 0, d_bytes, d_offs, n, d_out, nullptr);
+}
+int rgx_find_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t n,
+                       uint8_t* d_found, int64_t* d_out) {
+  return batch_dev(c, p, 1, d_bytes, d_offs, n, d_found, d_out);
+}
+
+static int batch_host(rgx_ctx* c, const rgx_program* p, int what, const uint8_t* bytes, const uint64_t* offs, uint64_t n,
+                      uint8_t* flag, int64_t* rec) {
+  if (!c || !p || (n && (!offs || !flag))) { set_error("null argument"); return RGX_EINVAL; }
+  if (n == 0) return RGX_OK;
+  if (what == 1 && p->prog.find_engine == FIND_NONE) {
+    set_error("FindBytes is not generated for a pattern without capture groups (regengo.go:110)");
+    return RGX_EUNSUPPORTED;
+  }
+  CU(cudaSetDevice(c->device));
+  const uint64_t base = offs[0], total = offs[n] - base;
+  int rc;
+  if ((rc = ensure(c, c->in_bytes, total + 16))) return rc;
+  if ((rc = ensure(c, c->in_offs, (n + 1) * 8))) return rc;
+  if ((rc = ensure(c, c->out_flag, n))) return rc;
+  const int nc = p->prog.prog.num_cap;
+  if (what == 1 && (rc = ensure(c, c->out_rec, n * nc * 8))) return rc;
+  if (total) CU(cudaMemcpyAsync(c->in_bytes.p, bytes + base, total, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->in_offs.p, offs, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  // offsets are used as given; shift the byte pointer so that offs[0] maps to the copied base
+  const uint8_t* d_bytes = (const uint8_t*)c->in_bytes.p - base;
+  rc = batch_dev(c, p, what, d_bytes, (const uint64_t*)c->in_offs.p, n, (uint8_t*)c->out_flag.p, (int64_t*)c->out_rec.p);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(flag, c->out_flag.p, n, cudaMemcpyDeviceToHost, c->stream));
+  if (what == 1) CU(cudaMemcpyAsync(rec, c->out_rec.p, n * nc * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
+}
+
+int rgx_match_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const uint64_t* offs, uint64_t n, uint8_t* out) {
+  return batch_host(c, p, 0, bytes, offs, n, out, nullptr);
+}
+int rgx_find_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const uint64_t* offs, uint64_t n, uint8_t* found,
+                   int64_t* out) {
+  if (n && !out) { set_error("null argument"); return RGX_EINVAL; }
+  return batch_host(c, p, 1, bytes, offs, n, found, out);
+}
+
+// ---- FindAllBytes -----------------------------------------------------------------------------------------
+static bool parallel_findall_ok(const DevMeta& m, const Program& P) {
+  if (m.flags & F_ANCHORED) return false;
+  if (m.find_engine == FIND_BT) return !(m.flags & F_FIND_MEMO);
+  if (m.find_engine == FIND_TDFA)
+    return P.tdfa.start_begin == P.tdfa.start_any && P.tdfa.init_tags_begin == P.tdfa.init_tags_any;
+  return false;
+}
+
+int64_t rgx_find_all_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t len, int64_t n_limit,
+                         int64_t* d_out, uint32_t* d_reps, uint64_t cap_records, uint64_t* n_records) {
+  if (!c || !p || !n_records) { set_error("null argument"); return RGX_EINVAL; }
+  *n_records = 0;
+  CU(cudaSetDevice(c->device));
+  const DeviceImage* im;
+  int rc = get_image(c, p, &im);
+  if (rc) return rc;
+  const DevMeta& m = im->meta;
+  if (m.find_engine == FIND_NONE) {
+    set_error("FindAllBytes is not generated for a pattern without capture groups (regengo.go:110)");
+    return RGX_EUNSUPPORTED;
+  }
+  if ((rc = check_caps(im, true))) return rc;
+  if (n_limit == 0 || len == 0) return 0;  // find.go:142-144; `searchStart >= l` / `offset < len(input)`
+  Small sm = small_of(c);
+  const size_t smem = im->in_smem ? (size_t)m.image_words * 4 : 0;
+  const int nc = m.find_engine == FIND_TDFA ? m.t_ntags : m.num_cap;
+
+  if (!parallel_findall_ok(m, p->prog)) {
+    ScratchPlan sp;
+    rc = plan_scratch(c, m, true, 1, len, 0, true, &sp);
+    if (rc) return rc;
+    if (sp.visited) CU(cudaMemsetAsync(sp.visited, 0, (size_t)sp.visited_words * 4, c->stream));
+    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
+    findall_sequential_kernel<<<1, 32, 0, c->stream>>>(m, im->d_words, d_buf, len, n_limit, d_out, d_reps, cap_records, sp, sm.slots, sm.err);
+    c->launches++;
+    CU(cudaGetLastError());
+    if ((rc = read_small(c, 256))) return rc;
+    const int e = *(int*)c->h_small;
+    if (e) { set_error("device engine scratch exhausted:" + err_bits(e)); return RGX_ENOMEM; }
+    const unsigned long long* t = (const unsigned long long*)((char*)c->h_small + 64);
+    *n_records = t[0];
+    if (t[0] > cap_records) { set_error("output capacity too small"); return RGX_ECAPACITY; }
+    return (int64_t)t[1];
+  }
+
+  const uint32_t mis = (uint32_t)((uintptr_t)d_buf & 15u);
+  const uint64_t cand_end = (uint64_t)mis + len + ((m.find_engine == FIND_TDFA && m.nullable) ? 1 : 0);
+  const uint64_t n_seg = (cand_end + SEG_BYTES - 1) / SEG_BYTES;
+  const uint32_t G = 32;
+  const uint64_t n_parts = (n_seg + G - 1) / G;
+
+  for (int attempt = 0; attempt < 12; attempt++) {
+    FindAllBufs fb;
+    fb.K = c->fa_K;
+    fb.cw = (uint32_t)std::max(nc - 2, 1);
+    if ((rc = ensure(c, c->fa_count, n_seg * 4))) return rc;
+    if ((rc = ensure(c, c->fa_keys, n_seg * fb.K * sizeof(uint2)))) return rc;
+    if ((rc = ensure(c, c->fa_caps, n_seg * fb.K * fb.cw * 4))) return rc;
+    if ((rc = ensure(c, c->fa_reps, n_seg * fb.K * 4))) return rc;
+    fb.count = (uint32_t*)c->fa_count.p; fb.keys = (uint2*)c->fa_keys.p; fb.caps = (int32_t*)c->fa_caps.p; fb.reps = (uint32_t*)c->fa_reps.p;
+    int grid = 0;
+    if (m.find_engine == FIND_TDFA) rc = occupancy_grid(c, findall_scan_kernel<FIND_TDFA>, SCAN_WARPS * 32, smem, &grid);
+    else rc = occupancy_grid(c, findall_scan_kernel<FIND_BT>, SCAN_WARPS * 32, smem, &grid);
+    if (rc) return rc;
+    const uint64_t need_blocks = (n_seg + SCAN_WARPS - 1) / SCAN_WARPS;
+    if ((uint64_t)grid > need_blocks) grid = (int)need_blocks;
+    ScratchPlan sp;
+    rc = plan_scratch(c, m, true, (uint32_t)grid * SCAN_WARPS * 32u, len, c->fa_stack_cap, false, &sp);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
+    if (m.find_engine == FIND_TDFA)
+      findall_scan_kernel<FIND_TDFA><<<grid, SCAN_WARPS * 32, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_buf, len, mis, n_seg, fb, sp, sm.err);
+    else
+      findall_scan_kernel<FIND_BT><<<grid, SCAN_WARPS * 32, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_buf, len, mis, n_seg, fb, sp, sm.err);
+    c->launches++;
+    CU(cudaGetLastError());
+
+    // chain passes
+    if ((rc = ensure(c, c->ch_a, n_parts * 8))) return rc;
+    if ((rc = ensure(c, c->ch_b, n_parts * 8))) return rc;
+    if ((rc = ensure(c, c->ch_sel, n_parts * 8))) return rc;
+    if ((rc = ensure(c, c->ch_reps, n_parts * 8))) return rc;
+    if ((rc = ensure(c, c->ch_selbase, n_parts * 8))) return rc;
+    if ((rc = ensure(c, c->ch_repsbase, n_parts * 8))) return rc;
+    ChainBufs cb;
+    cb.part_sel = (unsigned long long*)c->ch_sel.p; cb.part_reps = (unsigned long long*)c->ch_reps.p;
+    cb.changed = (int*)(sm.slots + 8);
+    long long* ex[2] = {(long long*)c->ch_a.p, (long long*)c->ch_b.p};
+    const int cgrid = (int)((n_parts + 127) / 128);
+    bool scan_failed = false;
+    for (int pass = 0;; pass++) {
+      cb.exit_cur = ex[pass & 1]; cb.exit_prev = ex[(pass + 1) & 1];
+      if (pass > 0) CU(cudaMemsetAsync(cb.changed, 0, sizeof(int), c->stream));
+      if (m.find_engine == FIND_TDFA)
+        findall_chain_kernel<FIND_TDFA><<<cgrid, 128, 0, c->stream>>>(n_seg, G, n_parts, mis, len, fb, cb, pass, sm.err);
+      else
+        findall_chain_kernel<FIND_BT><<<cgrid, 128, 0, c->stream>>>(n_seg, G, n_parts, mis, len, fb, cb, pass, sm.err);
+      c->launches++;
+      CU(cudaGetLastError());
+      if (pass == 0) {
+        if (n_parts == 1) break;
+        continue;
+      }
+      if ((rc = read_small(c, 256))) return rc;
+      const int e = *(int*)c->h_small;
+      if (e) { scan_failed = true; break; }
+      const int changed = *(int*)((char*)c->h_small + 64 + 8 * 8);
+      if (!changed) break;
+      if (pass > (int)n_parts + 2) { set_error("chain resolution did not converge"); return RGX_ECUDA; }
+    }
+    if (!scan_failed && n_parts == 1) {
+      if ((rc = read_small(c, 256))) return rc;
+      if (*(int*)c->h_small) scan_failed = true;
+    }
+    if (scan_failed) {
+      const int e = *(int*)c->h_small;
+      if (e & ERR_SLAB) { c->fa_K *= 2; continue; }
+      if (e & (ERR_STACK | ERR_CSTACK)) { c->fa_stack_cap *= 4; continue; }
+      set_error("device engine failure:" + err_bits(e));
+      return RGX_ENOMEM;
+    }
+    findall_part_scan_kernel<<<1, 1024, 0, c->stream>>>(n_parts, cb.part_sel, cb.part_reps, (unsigned long long*)c->ch_selbase.p,
+                                                        (unsigned long long*)c->ch_repsbase.p, sm.slots);
+    c->launches++;
+    CU(cudaMemsetAsync(sm.slots + 2, 0, 8, c->stream));
+    const int egrid = (int)((n_parts * 32 + 255) / 256);
+    if (m.find_engine == FIND_TDFA)
+      findall_emit_kernel<FIND_TDFA><<<egrid, 256, 0, c->stream>>>(m, n_seg, G, n_parts, mis, len, fb, (unsigned long long*)c->ch_selbase.p,
+                                                                   (unsigned long long*)c->ch_repsbase.p, n_limit, d_out, d_reps, cap_records, sm.slots + 2);
+    else
+      findall_emit_kernel<FIND_BT><<<egrid, 256, 0, c->stream>>>(m, n_seg, G, n_parts, mis, len, fb, (unsigned long long*)c->ch_selbase.p,
+                                                                 (unsigned long long*)c->ch_repsbase.p, n_limit, d_out, d_reps, cap_records, sm.slots + 2);
+    c->launches++;
+    CU(cudaGetLastError());
+    if ((rc = read_small(c, 256))) return rc;
+    const unsigned long long* t = (const unsigned long long*)((char*)c->h_small + 64);
+    unsigned long long total = t[1];
+    if (n_limit > 0 && total > (unsigned long long)n_limit) total = (unsigned long long)n_limit;
+    *n_records = t[2];
+    if (t[2] > cap_records) { set_error("output capacity too small"); return RGX_ECAPACITY; }
+    return (int64_t)total;
+  }
+  set_error("FindAll: could not size the record slabs / stacks for this input");
+  return RGX_ENOMEM;
+}
+
+int64_t rgx_find_all(rgx_ctx* c, const rgx_program* p, const uint8_t* buf, uint64_t len, int64_t n_limit, int64_t* out,
+                     uint64_t cap_matches) {
+  if (!c || !p || (len && !buf)) { set_error("null argument"); return RGX_EINVAL; }
+  if (p->prog.find_engine == FIND_NONE) {
+    set_error("FindAllBytes is not generated for a pattern without capture groups (regengo.go:110)");
+    return RGX_EUNSUPPORTED;
+  }
+  if (n_limit == 0 || len == 0) return 0;
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ensure(c, c->in_bytes, len + 16))) return rc;
+  CU(cudaMemcpyAsync(c->in_bytes.p, buf, len, cudaMemcpyHostToDevice, c->stream));
+  const int nc = p->prog.find_engine == FIND_TDFA ? p->prog.tdfa.num_tags : p->prog.prog.num_cap;
+  uint64_t cap_rec = std::max<uint64_t>(1024, std::min<uint64_t>(cap_matches, len / 16 + 1024));
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if ((rc = ensure(c, c->out_rec, cap_rec * nc * 8))) return rc;
+    if ((rc = ensure(c, c->out_reps, cap_rec * 4))) return rc;
+    uint64_t n_rec = 0;
+    int64_t total = rgx_find_all_dev(c, p, (const uint8_t*)c->in_bytes.p, len, n_limit, (int64_t*)c->out_rec.p,
+                                     (uint32_t*)c->out_reps.p, cap_rec, &n_rec);
+    if (total == RGX_ECAPACITY && attempt == 0) { cap_rec = n_rec; continue; }
+    if (total < 0) return total;
+    // run-length records -> the reference's flat list (repeats written out)
+    std::vector<int64_t> recs(n_rec * nc);
+    std::vector<uint32_t> reps(n_rec);
+    if (n_rec) {
+      CU(cudaMemcpyAsync(recs.data(), c->out_rec.p, n_rec * nc * 8, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(reps.data(), c->out_reps.p, n_rec * 4, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    uint64_t w = 0;
+    for (uint64_t j = 0; j < n_rec && w < cap_matches; j++)
+      for (uint32_t r = 0; r < reps[j] && w < cap_matches; r++, w++) std::memcpy(out + w * nc, &recs[j * nc], (size_t)nc * 8);
+    return total;
+  }
+  return RGX_ECAPACITY;
+}
+
+}  // extern "C"
+
+#include "capi_stream.inc"

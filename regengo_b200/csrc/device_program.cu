@@ -1,0 +1,199 @@
+// Host-side packing of a compiled Program into the device image (layout: device_program.cuh).
+#include "device_program.cuh"
+
+#include <cstring>
+#include <map>
+
+namespace rgx {
+
+namespace {
+
+struct Bits256 {
+  uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void set(uint32_t c) { w[(c & 255) >> 5] |= 1u << (c & 31); }
+  bool all() const { for (int i = 0; i < 8; i++) if (w[i] != 0xFFFFFFFFu) return false; return true; }
+};
+
+// Bytes that can be the first byte consumed by an attempt of the goto-machine, and whether the
+// attempt can reach Match without consuming anything.  Empty-width assertions are assumed to pass
+// (over-approximation: the set is only used to skip starts that cannot match).
+void first_bytes_bt(const Program& P, Bits256& first, bool& nullable) {
+  const Prog& prog = P.prog;
+  std::vector<uint8_t> seen(prog.inst.size(), 0);
+  std::vector<int> st{prog.start};
+  nullable = false;
+  while (!st.empty()) {
+    int pc = st.back(); st.pop_back();
+    if (seen[pc]) continue;
+    seen[pc] = 1;
+    const Inst& in = prog.inst[pc];
+    switch (in.op) {
+      case InstAlt: case InstAltMatch: st.push_back((int)in.out); st.push_back((int)in.arg); break;
+      case InstNop: case InstCapture: case InstEmptyWidth: st.push_back((int)in.out); break;
+      case InstMatch: nullable = true; break;
+      case InstFail: break;
+      case InstRune1: {
+        int32_t r = in.rune.empty() ? 0 : in.rune[0];
+        if (r < 128) first.set((uint32_t)r);
+        else if (r < 0x800) first.set(0xC0u | ((uint32_t)r >> 6));
+        else if (r < 0x10000) first.set(0xE0u | ((uint32_t)r >> 12));
+        else first.set(0xF0u | ((uint32_t)r >> 18));
+        break;
+      }
+      case InstRune:
+        for (int k = 0; k < 8; k++) first.w[k] |= P.class_bits[(size_t)pc * 8 + k];
+        if (P.unicode_class[pc]) for (uint32_t c = 128; c < 256; c++) first.set(c);
+        break;
+      case InstRuneAny: for (uint32_t c = 0; c < 256; c++) first.set(c); break;
+      case InstRuneAnyNotNL: for (uint32_t c = 0; c < 256; c++) if (c != '\n') first.set(c); break;
+    }
+  }
+}
+
+}  // namespace
+
+void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
+  std::memset(&m, 0, sizeof(m));
+  const Prog& prog = P.prog;
+  const uint32_t n = (uint32_t)prog.inst.size();
+  m.n_inst = (int32_t)n;
+  m.start = prog.start;
+  m.num_cap = prog.num_cap;
+  uint32_t f = 0;
+  if (P.anchored) f |= F_ANCHORED;
+  if (P.needs_backtracking) f |= F_NEEDS_BT;
+  if (P.has_prefix) f |= F_HAS_PREFIX;
+  if (P.match_memo) f |= F_MATCH_MEMO;
+  if (P.find_memo) f |= F_FIND_MEMO;
+  if (P.per_capture_ckpt) f |= F_PER_CAPTURE;
+  if (P.has_captures) f |= F_HAS_CAPTURES;
+  m.flags = (int32_t)f;
+  m.prefix = P.prefix;
+  m.match_engine = P.match_engine;
+  m.find_engine = P.find_engine;
+  w.clear();
+  auto align4 = [&]() { while (w.size() % 4) w.push_back(0); };
+
+  m.off_inst = (uint32_t)w.size();
+  for (uint32_t i = 0; i < n; i++) {
+    const Inst& in = prog.inst[i];
+    uint32_t fl = 0;
+    if (P.alt_ckpt[i]) fl |= IF_ALT_CKPT;
+    if (P.greedy_loop[i]) fl |= IF_GREEDY_LOOP;
+    if (P.unicode_class[i]) fl |= IF_UNICODE_CLASS;
+    if (P.char_state[i]) fl |= IF_CHAR_STATE;
+    if (in.op == InstAlt) m.n_alt++;
+    if (in.op == InstCapture) m.n_capinst++;
+    w.push_back((uint32_t)in.op | (fl << 8));
+    w.push_back(in.out);
+    w.push_back(in.arg);
+    w.push_back(in.op == InstRune1 && !in.rune.empty() ? (uint32_t)in.rune[0] : 0u);
+  }
+  m.off_cls = (uint32_t)w.size();
+  w.insert(w.end(), P.class_bits.begin(), P.class_bits.end());
+  m.off_th_eps = (uint32_t)w.size();
+  uint64_t char_mask = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    w.push_back((uint32_t)P.eps_after[i]);
+    w.push_back((uint32_t)(P.eps_after[i] >> 32));
+    if (P.char_state[i] && i < 64) char_mask |= 1ull << i;
+  }
+  m.off_th_cond = (uint32_t)w.size();
+  w.insert(w.end(), P.thompson_cond.begin(), P.thompson_cond.end());
+  m.th_start_lo = (uint32_t)P.start_closure; m.th_start_hi = (uint32_t)(P.start_closure >> 32);
+  m.th_accept_lo = (uint32_t)P.accept_mask; m.th_accept_hi = (uint32_t)(P.accept_mask >> 32);
+  m.th_char_lo = (uint32_t)char_mask; m.th_char_hi = (uint32_t)(char_mask >> 32);
+  // unicode ranges
+  m.off_rng_idx = (uint32_t)w.size();
+  {
+    std::vector<uint32_t> pairs;
+    for (uint32_t i = 0; i < n; i++) {
+      const Inst& in = prog.inst[i];
+      uint32_t first = (uint32_t)(pairs.size() / 2), cnt = 0;
+      if (in.op == InstRune && P.unicode_class[i])
+        for (size_t k = 0; k + 1 < in.rune.size(); k += 2) { pairs.push_back((uint32_t)in.rune[k]); pairs.push_back((uint32_t)in.rune[k + 1]); cnt++; }
+      w.push_back(first);
+      w.push_back(cnt);
+    }
+    m.off_rng_pairs = (uint32_t)w.size();
+    w.insert(w.end(), pairs.begin(), pairs.end());
+  }
+  align4();
+
+  // TDFA tables
+  Bits256 first;
+  bool nullable = false;
+  const Tdfa& t = P.tdfa;
+  if (t.built && P.find_engine == FIND_TDFA) {
+    m.t_ns = t.num_states; m.t_ntags = t.num_tags;
+    m.t_start_begin = t.start_begin; m.t_start_any = t.start_any;
+    m.t_n_init_begin = (int32_t)t.init_tags_begin.size(); m.t_n_init_any = (int32_t)t.init_tags_any.size();
+    // de-duplicated action lists; list 0 = empty
+    std::map<std::vector<uint32_t>, uint32_t> ids;
+    std::vector<std::vector<uint32_t>> lists;
+    auto list_id = [&](const std::vector<TagAction>& a) -> uint32_t {
+      std::vector<uint32_t> key;
+      for (const TagAction& x : a) key.push_back((uint32_t)x.tag | ((uint32_t)x.offset << 16));
+      auto it = ids.find(key);
+      if (it != ids.end()) return it->second;
+      uint32_t id = (uint32_t)lists.size();
+      ids[key] = id; lists.push_back(key);
+      return id;
+    };
+    list_id({});
+    m.off_t_trans = (uint32_t)w.size();
+    for (size_t i = 0; i < (size_t)t.num_states * 128; i++) {
+      uint32_t nx = t.trans[i] < 0 ? TDFA_NONE : (uint32_t)t.trans[i];
+      uint32_t al = t.trans[i] < 0 ? 0 : list_id(t.actions[i]);
+      w.push_back(nx | (al << 16));
+    }
+    m.off_t_accept = (uint32_t)w.size();
+    for (int s = 0; s < t.num_states; s++) {
+      uint32_t fl = (t.accept[s] ? 1u : 0u) | (t.accept_eot[s] ? 2u : 0u);
+      w.push_back(fl | (list_id(t.accept_actions[s]) << 16));
+    }
+    m.off_t_alist_off = (uint32_t)w.size();
+    {
+      uint32_t pos = 0;
+      for (auto& l : lists) { w.push_back(pos); pos += (uint32_t)l.size(); }
+      w.push_back(pos);
+    }
+    m.off_t_alist = (uint32_t)w.size();
+    for (auto& l : lists) w.insert(w.end(), l.begin(), l.end());
+    m.off_t_init = (uint32_t)w.size();
+    for (int x : t.init_tags_begin) w.push_back((uint32_t)x);
+    for (int x : t.init_tags_any) w.push_back((uint32_t)x);
+    align4();
+    // start filter from the tables: bytes with a transition out of startStateAny
+    nullable = t.accept[t.start_any] || t.accept_eot[t.start_any];
+    for (uint32_t c = 0; c < 128; c++) if (t.trans[(size_t)t.start_any * 128 + c] >= 0) first.set(c);
+    int s = t.start_any;
+    while (m.prefix_len < MAX_PREFIX && !t.accept[s] && !t.accept_eot[s]) {
+      int only = -1, cnt = 0;
+      for (int c = 0; c < 128; c++) if (t.trans[(size_t)s * 128 + c] >= 0) { only = c; cnt++; }
+      if (cnt != 1) break;
+      m.prefix_bytes[m.prefix_len++] = (uint8_t)only;
+      s = t.trans[(size_t)s * 128 + only];
+    }
+  } else {
+    first_bytes_bt(P, first, nullable);
+    int pc = prog.start;
+    for (size_t guard = 0; guard <= n && m.prefix_len < MAX_PREFIX; guard++) {
+      const Inst& in = prog.inst[pc];
+      if (in.op == InstNop || in.op == InstCapture) { pc = (int)in.out; continue; }
+      if (in.op == InstRune1 && in.rune.size() == 1 && in.rune[0] < 128) { m.prefix_bytes[m.prefix_len++] = (uint8_t)in.rune[0]; pc = (int)in.out; continue; }
+      break;
+    }
+  }
+  m.nullable = nullable ? 1 : 0;
+  m.off_first = (uint32_t)w.size();
+  for (int k = 0; k < 8; k++) w.push_back(first.w[k]);
+  align4();
+  if (nullable) { m.gen_kind = GEN_ALL; m.prefix_len = 0; }
+  else if (m.prefix_len > 0) m.gen_kind = GEN_PREFIX;
+  else if (!first.all()) m.gen_kind = GEN_BYTESET;
+  else m.gen_kind = GEN_ALL;
+  m.image_words = (uint32_t)w.size();
+}
+
+}  // namespace rgx

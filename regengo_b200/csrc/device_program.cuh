@@ -1,0 +1,94 @@
+// Device-side form of one compiled pattern: a packed table image (u32 words, 16-byte aligned)
+// that every CTA stages from HBM/L2 into shared memory with ONE TMA bulk copy
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), plus a small by-value DevMeta
+// with the scalars and the section offsets.
+//
+// The image holds what the reference bakes into generated Go source: the instruction list of the
+// goto-machine (internal/compiler/instructions.go), the class bitmaps (charclass.go:43-74), the
+// Thompson closure masks (thompson.go:133-157) and the TDFA tables (tdfa.go:547-794), re-packed
+// for the GPU: 16-byte instruction records, u32 transition cells carrying the next state and the
+// index of a de-duplicated tag-action list.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "blob.hpp"
+
+namespace rgx {
+
+constexpr int MAX_CAPS = 32;         // 2*(k+1) <= 32 on the device paths
+constexpr int MAX_PREFIX = 8;
+constexpr uint32_t TDFA_NONE = 0xFFFFu;
+constexpr uint32_t SMEM_IMAGE_LIMIT = 160 * 1024;
+
+enum GenKind : int { GEN_ALL = 0, GEN_BYTESET = 1, GEN_PREFIX = 2 };
+
+struct DevMeta {
+  int32_t n_inst, start, num_cap, flags, prefix, match_engine, find_engine;
+  uint32_t image_words;        // multiple of 4
+  uint32_t off_inst, off_cls, off_th_eps, off_th_cond, off_rng_idx, off_rng_pairs;
+  uint32_t off_t_trans, off_t_accept, off_t_alist_off, off_t_alist, off_t_init, off_first;
+  int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
+  uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;
+  // FindAll candidate generator (start filter); see findall_kernels.cu
+  int32_t gen_kind, prefix_len;
+  uint8_t prefix_bytes[MAX_PREFIX];
+  int32_t nullable;            // a match attempt can succeed without consuming input
+  int32_t n_alt;               // number of Alt instructions (stack sizing)
+  int32_t n_capinst;
+};
+
+struct DeviceImage {
+  DevMeta meta;
+  uint32_t* d_words = nullptr;  // device copy of the image
+  bool in_smem = true;          // image fits the shared-memory budget
+};
+
+// host: build image words + meta from a Program (device_program.cu)
+void pack_program(const Program& P, std::vector<uint32_t>& words, DevMeta& meta);
+
+#ifdef __CUDACC__
+// View over the staged image.
+struct DProg {
+  const uint32_t* img;
+  __device__ __forceinline__ uint4 inst(const DevMeta& m, int pc) const {
+    return reinterpret_cast<const uint4*>(img + m.off_inst)[pc];
+  }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Stage the image into shared memory with a 1-D TMA bulk copy.  `mbar` is an 8-byte aligned
+// shared u64.  All threads of the CTA must call this; returns after the bytes have landed.
+__device__ __forceinline__ void stage_image_tma(uint32_t* smem_dst, const uint32_t* gsrc, uint32_t words,
+                                                unsigned long long* mbar) {
+  const uint32_t bytes = words * 4u;
+  const uint32_t bar = smem_u32(mbar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar)
+        : "memory");
+  }
+}
+#endif
+
+}  // namespace rgx

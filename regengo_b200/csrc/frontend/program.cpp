@@ -650,6 +650,34 @@ bool build_program(const std::string& pattern, const Options& opts, Program& P, 
       if (in.out < n) P.eps_after[i] = P.closures[in.out];
     }
   }
+  // Thompson per-state byte conditions (thompson.go:199-303): the condition is on the BYTE c.
+  P.thompson_cond.assign(n * 8, 0);
+  for (size_t i = 0; i < n; i++) {
+    const Inst& in = prog.inst[i];
+    auto set = [&](uint32_t c) { P.thompson_cond[i * 8 + ((c & 255) >> 5)] |= 1u << (c & 31); };
+    if (in.op == InstRune1) {
+      if (!in.rune.empty()) set((uint32_t)in.rune[0] & 255u);            // byte(r): truncated (Q9)
+    } else if (in.op == InstRuneAny) {
+      for (uint32_t c = 0; c < 256; c++) set(c);
+    } else if (in.op == InstRuneAnyNotNL) {
+      for (uint32_t c = 0; c < 256; c++) if (c != '\n') set(c);
+    } else if (in.op == InstRune) {
+      const auto& r = in.rune;
+      bool fold = (in.arg & FoldCase) != 0;
+      if (r.size() == 2 && r[0] == r[1]) {
+        if (fold && r[0] < 128) { for (uint32_t c = 0; c < 256; c++) if ((c | 0x20u) == (uint32_t)(r[0] | 0x20)) set(c); }
+        else set((uint32_t)r[0] & 255u);
+      } else {
+        for (size_t k = 0; k + 1 < r.size(); k += 2) {
+          int32_t lo = r[k], hi = r[k + 1];
+          if (lo >= 128) continue;
+          if (lo == hi) { set((uint32_t)lo); continue; }
+          if (hi > 127) hi = 127;
+          for (int32_t c = lo; c <= hi; c++) set((uint32_t)c);
+        }
+      }
+    }
+  }
   derive_labels(P, ast);
   return true;
 }
@@ -709,6 +737,7 @@ std::string program_to_json(const Program& P) {
   o << "],\"eps_after\":[";
   for (size_t i = 0; i < P.eps_after.size(); i++) { if (i) o << ','; o << '"' << P.eps_after[i] << '"'; }
   o << "],\"char_state\":"; jarr(o, P.char_state);
+  o << ",\"thompson_cond\":"; jarr(o, P.thompson_cond);
   o << ",\"engine_labels\":[";
   for (size_t i = 0; i < P.engine_labels.size(); i++) { if (i) o << ','; jstr(o, P.engine_labels[i]); }
   o << "],\"feature_labels\":[";

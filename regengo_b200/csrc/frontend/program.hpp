@@ -71,6 +71,7 @@ struct Program {
   std::vector<uint64_t> closures;      // [n_inst]
   std::vector<uint64_t> eps_after;     // [n_inst] = closures[Inst[i].Out] for char states else 0
   std::vector<uint8_t> char_state;     // [n_inst]
+  std::vector<uint32_t> thompson_cond; // [n_inst*8] byte set of the per-state condition (thompson.go:199-303)
   // TDFA
   Tdfa tdfa;
   // Analyze() labels (analyze_api.go)

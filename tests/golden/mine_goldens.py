@@ -163,7 +163,7 @@ def mine_thompson(body):
     out["anchored"] = "Anchored pattern" in body
     # per-state byte conditions
     conds = {}
-    for bit, cond in re.findall(r"if current&uint64\((0x[0-9a-f]+)\) != 0 && (.*) \{\n", body):
+    for bit, cond in re.findall(r"if current&uint64\(uint64\((0x[0-9a-f]+)\)\) != 0 && (.*) \{\n", body):
         state = int(bit, 16).bit_length() - 1
         py = go_cond_to_py(cond)
         code = compile(py, "<cond>", "eval")
