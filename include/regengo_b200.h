@@ -97,6 +97,10 @@ int rgx_ctx_create(int32_t device, rgx_ctx** out);
 void rgx_ctx_destroy(rgx_ctx* c);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 int64_t rgx_ctx_launches(const rgx_ctx* c);
+/* Per-phase device timing of the last rgx_find_all*_dev call (CUDA events recorded on the context's
+ * stream): out_ms[4] = {scan kernel, chain kernels, compaction kernels, all three}. */
+int rgx_ctx_enable_timing(rgx_ctx* c, int32_t on);
+int rgx_ctx_last_timing(const rgx_ctx* c, float* out_ms);
 /* The context's CUDA stream as an opaque cudaStream_t, for event timing on the launching stream. */
 void* rgx_ctx_stream(const rgx_ctx* c);
 int rgx_ctx_sync(rgx_ctx* c);
@@ -126,6 +130,14 @@ int rgx_find_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes,
  *      (SURVEY.md Q2); repeats are written out as individual records here.                      */
 int64_t rgx_find_all(rgx_ctx* c, const rgx_program* p, const uint8_t* buf, uint64_t len,
                      int64_t n_limit, int64_t* out_offsets, uint64_t cap_matches);
+
+/* Host buffers, run-length result: record j (out_offsets[j*2(k+1)..]) is one distinct match and
+ * out_reps[j] how many consecutive times FindAllBytes returns it (always 1 for the backtracking
+ * engine; > 1 only under the TDFA stride rule).  A cgo shim appends the same *TBytesResult
+ * out_reps[j] times.  Return value / n_records / RGX_ECAPACITY as for rgx_find_all_dev.          */
+int64_t rgx_find_all_rle(rgx_ctx* c, const rgx_program* p, const uint8_t* buf, uint64_t len,
+                         int64_t n_limit, int64_t* out_offsets, uint32_t* out_reps,
+                         uint64_t cap_records, uint64_t* n_records);
 
 /* Device-resident form.  Results stay on the device in run-length form: record j is the offset
  * record of one distinct match and d_reps[j] how many consecutive times the reference returns

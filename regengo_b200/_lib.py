@@ -37,6 +37,8 @@ _SIGS = {
     "rgx_ctx_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
     "rgx_ctx_destroy": (None, [_P]),
     "rgx_ctx_launches": (C.c_int64, [_P]),
+    "rgx_ctx_enable_timing": (C.c_int, [_P, C.c_int32]),
+    "rgx_ctx_last_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rgx_ctx_stream": (_P, [_P]),
     "rgx_ctx_sync": (C.c_int, [_P]),
     "rgx_match_batch": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
@@ -44,6 +46,7 @@ _SIGS = {
     "rgx_find_batch": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
     "rgx_find_batch_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
     "rgx_find_all": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, C.c_uint64]),
+    "rgx_find_all_rle": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rgx_find_all_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rgx_find_reader": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_uint64]),
     "rgx_find_reader_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

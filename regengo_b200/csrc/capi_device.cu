@@ -14,6 +14,8 @@
 #include "engines.cuh"
 #include "kernels_batch.cuh"
 #include "kernels_findall.cuh"
+#include "kernels_findall2.cuh"
+#include "kernels_chain.cuh"
 #include "kernels_stream.cuh"
 
 using namespace rgx;
@@ -34,10 +36,14 @@ struct rgx_ctx {
   int64_t launches = 0;
   // grow-only scratch
   DevBuf stack, cstack, visited, small, in_bytes, in_offs, out_flag, out_rec, out_reps, out_aux;
-  DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase;
+  DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase, ch_segsel, ch_segreps;
   void* h_small = nullptr;  // pinned, 4 KiB
   uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
   uint32_t fa_stack_cap = 256;
+  // optional per-phase timing of the last FindAll (CUDA events on the launching stream)
+  bool timing = false;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float last_ms[4] = {0, 0, 0, 0};  // scan, chain, emit, total
 };
 
 namespace {
@@ -103,7 +109,8 @@ int check_caps(const DeviceImage* im, bool find) {
 
 template <class K>
 int occupancy_grid(rgx_ctx* c, K kernel, int block, size_t smem, int* grid) {
-  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // static + dynamic shared memory above 48 KiB needs the opt-in, so always declare the dynamic size
+  if (smem > 0) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
   if (per_sm < 1) per_sm = 1;
@@ -214,14 +221,28 @@ void rgx_ctx_destroy(rgx_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->stack, &c->cstack, &c->visited, &c->small, &c->in_bytes, &c->in_offs, &c->out_flag, &c->out_rec,
                     &c->out_reps, &c->out_aux, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
-                    &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase};
+                    &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase, &c->ch_segsel, &c->ch_segreps};
   for (DevBuf* b : bufs) free_buf(*b);
   if (c->h_small) cudaFreeHost(c->h_small);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 int64_t rgx_ctx_launches(const rgx_ctx* c) { return c ? c->launches : 0; }
+
+int rgx_ctx_enable_timing(rgx_ctx* c, int32_t on) {
+  if (!c) return RGX_EINVAL;
+  CU(cudaSetDevice(c->device));
+  if (on && !c->ev[0]) for (auto& e : c->ev) CU(cudaEventCreate(&e));
+  c->timing = on != 0;
+  return RGX_OK;
+}
+int rgx_ctx_last_timing(const rgx_ctx* c, float* out_ms) {
+  if (!c || !out_ms) return RGX_EINVAL;
+  for (int i = 0; i < 4; i++) out_ms[i] = c->last_ms[i];
+  return RGX_OK;
+}
 void* rgx_ctx_stream(const rgx_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int rgx_ctx_sync(rgx_ctx* c) {
   if (!c) return RGX_EINVAL;
@@ -356,191 +377,7 @@ int rgx_find_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const
   return batch_host(c, p, 1, bytes, offs, n, found, out);
 }
 
-// ---- FindAllBytes -----------------------------------------------------------------------------------------
-static bool parallel_findall_ok(const DevMeta& m, const Program& P) {
-  if (m.flags & F_ANCHORED) return false;
-  if (m.find_engine == FIND_BT) return !(m.flags & F_FIND_MEMO);
-  if (m.find_engine == FIND_TDFA)
-    return P.tdfa.start_begin == P.tdfa.start_any && P.tdfa.init_tags_begin == P.tdfa.init_tags_any;
-  return false;
-}
-
-int64_t rgx_find_all_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t len, int64_t n_limit,
-                         int64_t* d_out, uint32_t* d_reps, uint64_t cap_records, uint64_t* n_records) {
-  if (!c || !p || !n_records) { set_error("null argument"); return RGX_EINVAL; }
-  *n_records = 0;
-  CU(cudaSetDevice(c->device));
-  const DeviceImage* im;
-  int rc = get_image(c, p, &im);
-  if (rc) return rc;
-  const DevMeta& m = im->meta;
-  if (m.find_engine == FIND_NONE) {
-    set_error("FindAllBytes is not generated for a pattern without capture groups (regengo.go:110)");
-    return RGX_EUNSUPPORTED;
-  }
-  if ((rc = check_caps(im, true))) return rc;
-  if (n_limit == 0 || len == 0) return 0;  // find.go:142-144; `searchStart >= l` / `offset < len(input)`
-  Small sm = small_of(c);
-  const size_t smem = im->in_smem ? (size_t)m.image_words * 4 : 0;
-  const int nc = m.find_engine == FIND_TDFA ? m.t_ntags : m.num_cap;
-
-  if (!parallel_findall_ok(m, p->prog)) {
-    ScratchPlan sp;
-    rc = plan_scratch(c, m, true, 1, len, 0, true, &sp);
-    if (rc) return rc;
-    if (sp.visited) CU(cudaMemsetAsync(sp.visited, 0, (size_t)sp.visited_words * 4, c->stream));
-    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
-    findall_sequential_kernel<<<1, 32, 0, c->stream>>>(m, im->d_words, d_buf, len, n_limit, d_out, d_reps, cap_records, sp, sm.slots, sm.err);
-    c->launches++;
-    CU(cudaGetLastError());
-    if ((rc = read_small(c, 256))) return rc;
-    const int e = *(int*)c->h_small;
-    if (e) { set_error("device engine scratch exhausted:" + err_bits(e)); return RGX_ENOMEM; }
-    const unsigned long long* t = (const unsigned long long*)((char*)c->h_small + 64);
-    *n_records = t[0];
-    if (t[0] > cap_records) { set_error("output capacity too small"); return RGX_ECAPACITY; }
-    return (int64_t)t[1];
-  }
-
-  const uint32_t mis = (uint32_t)((uintptr_t)d_buf & 15u);
-  const uint64_t cand_end = (uint64_t)mis + len + ((m.find_engine == FIND_TDFA && m.nullable) ? 1 : 0);
-  const uint64_t n_seg = (cand_end + SEG_BYTES - 1) / SEG_BYTES;
-  const uint32_t G = 32;
-  const uint64_t n_parts = (n_seg + G - 1) / G;
-
-  for (int attempt = 0; attempt < 12; attempt++) {
-    FindAllBufs fb;
-    fb.K = c->fa_K;
-    fb.cw = (uint32_t)std::max(nc - 2, 1);
-    if ((rc = ensure(c, c->fa_count, n_seg * 4))) return rc;
-    if ((rc = ensure(c, c->fa_keys, n_seg * fb.K * sizeof(uint2)))) return rc;
-    if ((rc = ensure(c, c->fa_caps, n_seg * fb.K * fb.cw * 4))) return rc;
-    if ((rc = ensure(c, c->fa_reps, n_seg * fb.K * 4))) return rc;
-    fb.count = (uint32_t*)c->fa_count.p; fb.keys = (uint2*)c->fa_keys.p; fb.caps = (int32_t*)c->fa_caps.p; fb.reps = (uint32_t*)c->fa_reps.p;
-    int grid = 0;
-    if (m.find_engine == FIND_TDFA) rc = occupancy_grid(c, findall_scan_kernel<FIND_TDFA>, SCAN_WARPS * 32, smem, &grid);
-    else rc = occupancy_grid(c, findall_scan_kernel<FIND_BT>, SCAN_WARPS * 32, smem, &grid);
-    if (rc) return rc;
-    const uint64_t need_blocks = (n_seg + SCAN_WARPS - 1) / SCAN_WARPS;
-    if ((uint64_t)grid > need_blocks) grid = (int)need_blocks;
-    ScratchPlan sp;
-    rc = plan_scratch(c, m, true, (uint32_t)grid * SCAN_WARPS * 32u, len, c->fa_stack_cap, false, &sp);
-    if (rc) return rc;
-    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
-    if (m.find_engine == FIND_TDFA)
-      findall_scan_kernel<FIND_TDFA><<<grid, SCAN_WARPS * 32, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_buf, len, mis, n_seg, fb, sp, sm.err);
-    else
-      findall_scan_kernel<FIND_BT><<<grid, SCAN_WARPS * 32, smem, c->stream>>>(m, im->d_words, im->in_smem ? 1 : 0, d_buf, len, mis, n_seg, fb, sp, sm.err);
-    c->launches++;
-    CU(cudaGetLastError());
-
-    // chain passes
-    if ((rc = ensure(c, c->ch_a, n_parts * 8))) return rc;
-    if ((rc = ensure(c, c->ch_b, n_parts * 8))) return rc;
-    if ((rc = ensure(c, c->ch_sel, n_parts * 8))) return rc;
-    if ((rc = ensure(c, c->ch_reps, n_parts * 8))) return rc;
-    if ((rc = ensure(c, c->ch_selbase, n_parts * 8))) return rc;
-    if ((rc = ensure(c, c->ch_repsbase, n_parts * 8))) return rc;
-    ChainBufs cb;
-    cb.part_sel = (unsigned long long*)c->ch_sel.p; cb.part_reps = (unsigned long long*)c->ch_reps.p;
-    cb.changed = (int*)(sm.slots + 8);
-    long long* ex[2] = {(long long*)c->ch_a.p, (long long*)c->ch_b.p};
-    const int cgrid = (int)((n_parts + 127) / 128);
-    bool scan_failed = false;
-    for (int pass = 0;; pass++) {
-      cb.exit_cur = ex[pass & 1]; cb.exit_prev = ex[(pass + 1) & 1];
-      if (pass > 0) CU(cudaMemsetAsync(cb.changed, 0, sizeof(int), c->stream));
-      if (m.find_engine == FIND_TDFA)
-        findall_chain_kernel<FIND_TDFA><<<cgrid, 128, 0, c->stream>>>(n_seg, G, n_parts, mis, len, fb, cb, pass, sm.err);
-      else
-        findall_chain_kernel<FIND_BT><<<cgrid, 128, 0, c->stream>>>(n_seg, G, n_parts, mis, len, fb, cb, pass, sm.err);
-      c->launches++;
-      CU(cudaGetLastError());
-      if (pass == 0) {
-        if (n_parts == 1) break;
-        continue;
-      }
-      if ((rc = read_small(c, 256))) return rc;
-      const int e = *(int*)c->h_small;
-      if (e) { scan_failed = true; break; }
-      const int changed = *(int*)((char*)c->h_small + 64 + 8 * 8);
-      if (!changed) break;
-      if (pass > (int)n_parts + 2) { set_error("chain resolution did not converge"); return RGX_ECUDA; }
-    }
-    if (!scan_failed && n_parts == 1) {
-      if ((rc = read_small(c, 256))) return rc;
-      if (*(int*)c->h_small) scan_failed = true;
-    }
-    if (scan_failed) {
-      const int e = *(int*)c->h_small;
-      if (e & ERR_SLAB) { c->fa_K *= 2; continue; }
-      if (e & (ERR_STACK | ERR_CSTACK)) { c->fa_stack_cap *= 4; continue; }
-      set_error("device engine failure:" + err_bits(e));
-      return RGX_ENOMEM;
-    }
-    findall_part_scan_kernel<<<1, 1024, 0, c->stream>>>(n_parts, cb.part_sel, cb.part_reps, (unsigned long long*)c->ch_selbase.p,
-                                                        (unsigned long long*)c->ch_repsbase.p, sm.slots);
-    c->launches++;
-    CU(cudaMemsetAsync(sm.slots + 2, 0, 8, c->stream));
-    const int egrid = (int)((n_parts * 32 + 255) / 256);
-    if (m.find_engine == FIND_TDFA)
-      findall_emit_kernel<FIND_TDFA><<<egrid, 256, 0, c->stream>>>(m, n_seg, G, n_parts, mis, len, fb, (unsigned long long*)c->ch_selbase.p,
-                                                                   (unsigned long long*)c->ch_repsbase.p, n_limit, d_out, d_reps, cap_records, sm.slots + 2);
-    else
-      findall_emit_kernel<FIND_BT><<<egrid, 256, 0, c->stream>>>(m, n_seg, G, n_parts, mis, len, fb, (unsigned long long*)c->ch_selbase.p,
-                                                                 (unsigned long long*)c->ch_repsbase.p, n_limit, d_out, d_reps, cap_records, sm.slots + 2);
-    c->launches++;
-    CU(cudaGetLastError());
-    if ((rc = read_small(c, 256))) return rc;
-    const unsigned long long* t = (const unsigned long long*)((char*)c->h_small + 64);
-    unsigned long long total = t[1];
-    if (n_limit > 0 && total > (unsigned long long)n_limit) total = (unsigned long long)n_limit;
-    *n_records = t[2];
-    if (t[2] > cap_records) { set_error("output capacity too small"); return RGX_ECAPACITY; }
-    return (int64_t)total;
-  }
-  set_error("FindAll: could not size the record slabs / stacks for this input");
-  return RGX_ENOMEM;
-}
-
-int64_t rgx_find_all(rgx_ctx* c, const rgx_program* p, const uint8_t* buf, uint64_t len, int64_t n_limit, int64_t* out,
-                     uint64_t cap_matches) {
-  if (!c || !p || (len && !buf)) { set_error("null argument"); return RGX_EINVAL; }
-  if (p->prog.find_engine == FIND_NONE) {
-    set_error("FindAllBytes is not generated for a pattern without capture groups (regengo.go:110)");
-    return RGX_EUNSUPPORTED;
-  }
-  if (n_limit == 0 || len == 0) return 0;
-  CU(cudaSetDevice(c->device));
-  int rc;
-  if ((rc = ensure(c, c->in_bytes, len + 16))) return rc;
-  CU(cudaMemcpyAsync(c->in_bytes.p, buf, len, cudaMemcpyHostToDevice, c->stream));
-  const int nc = p->prog.find_engine == FIND_TDFA ? p->prog.tdfa.num_tags : p->prog.prog.num_cap;
-  uint64_t cap_rec = std::max<uint64_t>(1024, std::min<uint64_t>(cap_matches, len / 16 + 1024));
-  for (int attempt = 0; attempt < 2; attempt++) {
-    if ((rc = ensure(c, c->out_rec, cap_rec * nc * 8))) return rc;
-    if ((rc = ensure(c, c->out_reps, cap_rec * 4))) return rc;
-    uint64_t n_rec = 0;
-    int64_t total = rgx_find_all_dev(c, p, (const uint8_t*)c->in_bytes.p, len, n_limit, (int64_t*)c->out_rec.p,
-                                     (uint32_t*)c->out_reps.p, cap_rec, &n_rec);
-    if (total == RGX_ECAPACITY && attempt == 0) { cap_rec = n_rec; continue; }
-    if (total < 0) return total;
-    // run-length records -> the reference's flat list (repeats written out)
-    std::vector<int64_t> recs(n_rec * nc);
-    std::vector<uint32_t> reps(n_rec);
-    if (n_rec) {
-      CU(cudaMemcpyAsync(recs.data(), c->out_rec.p, n_rec * nc * 8, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaMemcpyAsync(reps.data(), c->out_reps.p, n_rec * 4, cudaMemcpyDeviceToHost, c->stream));
-      CU(cudaStreamSynchronize(c->stream));
-    }
-    uint64_t w = 0;
-    for (uint64_t j = 0; j < n_rec && w < cap_matches; j++)
-      for (uint32_t r = 0; r < reps[j] && w < cap_matches; r++, w++) std::memcpy(out + w * nc, &recs[j * nc], (size_t)nc * 8);
-    return total;
-  }
-  return RGX_ECAPACITY;
-}
-
 }  // extern "C"
 
+#include "capi_findall.inc"
 #include "capi_stream.inc"

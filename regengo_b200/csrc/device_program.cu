@@ -164,6 +164,19 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     for (int x : t.init_tags_begin) w.push_back((uint32_t)x);
     for (int x : t.init_tags_any) w.push_back((uint32_t)x);
     align4();
+    // fast cells: everything one walk step needs in a single shared-memory word
+    if (t.num_states < (int)FAST_NONE && lists.size() <= 1023) {
+      m.off_t_fast = (uint32_t)w.size();
+      for (size_t i = 0; i < (size_t)t.num_states * 128; i++) {
+        if (t.trans[i] < 0) { w.push_back(FAST_NONE); continue; }
+        const int nx = t.trans[i];
+        uint32_t cell = (uint32_t)nx | (list_id(t.actions[i]) << 10) | (list_id(t.accept_actions[nx]) << 20);
+        if (t.accept[nx]) cell |= 1u << 30;
+        if (t.accept_eot[nx]) cell |= 1u << 31;
+        w.push_back(cell);
+      }
+      align4();
+    }
     // start filter from the tables: bytes with a transition out of startStateAny
     nullable = t.accept[t.start_any] || t.accept_eot[t.start_any];
     for (uint32_t c = 0; c < 128; c++) if (t.trans[(size_t)t.start_any * 128 + c] >= 0) first.set(c);

@@ -21,6 +21,7 @@ namespace rgx {
 constexpr int MAX_CAPS = 32;         // 2*(k+1) <= 32 on the device paths
 constexpr int MAX_PREFIX = 8;
 constexpr uint32_t TDFA_NONE = 0xFFFFu;
+constexpr uint32_t FAST_NONE = 0x3FFu;   // next-state field of a fast cell with no transition
 constexpr uint32_t SMEM_IMAGE_LIMIT = 160 * 1024;
 
 enum GenKind : int { GEN_ALL = 0, GEN_BYTESET = 1, GEN_PREFIX = 2 };
@@ -30,6 +31,8 @@ struct DevMeta {
   uint32_t image_words;        // multiple of 4
   uint32_t off_inst, off_cls, off_th_eps, off_th_cond, off_rng_idx, off_rng_pairs;
   uint32_t off_t_trans, off_t_accept, off_t_alist_off, off_t_alist, off_t_init, off_first;
+  // "fast" TDFA cells (0 = absent): next:10 | transition alist:10 | accept alist of NEXT:10 | next accepts:1 | next accepts at EOT:1
+  uint32_t off_t_fast;
   int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
   uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;
   // FindAll candidate generator (start filter); see findall_kernels.cu
