@@ -1,0 +1,98 @@
+"""stream.FindReader parity: the chunk-parallel CUDA path (through the C ABI) against the oracle's
+literal emulation of the reference loop (leftover carry, deferral, bytes.Index).  Needs a GPU."""
+import io
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import regengo_b200 as rg  # noqa: E402
+from regengo_b200 import synth  # noqa: E402
+from oracle import Oracle  # noqa: E402
+
+
+def pair(pattern, **kw):
+    p = rg.Pattern(pattern, **kw)
+    return p, Oracle(p.blob())
+
+
+def check_reader(p, o, data, buffer_size=0, max_leftover=0):
+    n, so, ci, recs = p.find_reader_offsets(data, rg.StreamConfig(buffer_size, max_leftover))
+    en, eso, eci, erecs = o.find_reader(data, buffer_size, max_leftover)
+    assert n == en, (n, en)
+    assert np.array_equal(so, eso)
+    assert np.array_equal(ci, eci)
+    assert np.array_equal(recs, erecs)
+    return n
+
+
+def test_reference_stream_kats():
+    # tests/integration/streaming/streaming_test.go:190-316 through the device path
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    pos = [100, 32768, 65530, 65550, 70000, 99000]
+    dates = [b"2024-01-01", b"2024-02-02", b"2024-03-03", b"2024-04-04", b"2024-05-05", b"2024-06-06"]
+    buf = bytearray(b"x" * (100 * 1024))
+    for q, d in zip(pos, dates):
+        buf[q:q + 10] = d
+    n, so, ci, recs = p.find_reader_offsets(bytes(buf), rg.StreamConfig(64 * 1024, 0))
+    assert n == 6 and so.tolist() == pos and ci.tolist() == [0, 0, 1, 1, 1, 1]
+    check_reader(p, o, bytes(buf), 64 * 1024)
+    data = b"prefix 2024-01-15 middle 2024-02-20 suffix"
+    n, so, _, _ = p.find_reader_offsets(data)
+    assert so.tolist() == [7, 25]
+    # early termination is the callback's business (streaming_test.go:143-162)
+    seen = []
+    p.find_reader(io.BytesIO(b"2024-01-01 " * 100), rg.StreamConfig(), lambda m: (seen.append(m.stream_offset) or len(seen) < 5))
+    assert seen == [0, 11, 22, 33, 44]
+    assert p.find_reader_count(io.BytesIO(b"x" * 10000)) == 0
+    assert p.find_reader_count(io.BytesIO(b"")) == 0
+    with pytest.raises(rg.BufferTooSmall):
+        p.find_reader_offsets(b"abc", rg.StreamConfig(1000, 0))
+
+
+@pytest.mark.parametrize("digit_noise", [0.0, 0.02])
+@pytest.mark.parametrize("bufsize,leftover", [(0, 0), (65536, 4096), (1 << 17, 0)])
+def test_patterned_stream(digit_noise, bufsize, leftover):
+    # configs[4] at oracle-friendly size, with and without the digit noise that fires the skip-restart rule
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    buf = synth.make_buffer("stream", 3 * synth.BLOCK + 4321, digit_noise=digit_noise)
+    n = check_reader(p, o, buf, bufsize, leftover)
+    assert n > 50000
+
+
+def test_exact_fill_flush_pass_and_short_streams():
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    B, L = 65536, 1024
+    stride = B - L
+    base = synth.make_buffer("stream", 4 * B, digit_noise=0.02)
+    for total in (B, B + stride, B + 2 * stride, B - 1, B + 1, L, L + 1, 10, 1, B + stride - 1, 2 * B):
+        check_reader(p, o, base[:total], B, L)
+
+
+def test_q15_q16_quirks_on_device():
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    buf = bytearray(b"x" * (100 * 1024))
+    buf[64505:64515] = b"2024-01-15"
+    assert check_reader(p, o, bytes(buf), 65536) == 0          # straddles the deferral line: dropped
+    assert check_reader(p, o, b"12024-01-15 2024-01-15") == 2   # bytes.Index reports the skipped text first
+
+
+def test_tdfa_and_backtracking_patterns_streaming():
+    for pat, kind in ((synth.URL_PATTERN, "url"), (synth.EMAIL_PATTERN, "log"), (r"(\d+)", "stream")):
+        p, o = pair(pat)
+        buf = synth.make_buffer(kind, 300_000)
+        check_reader(p, o, buf)
+        check_reader(p, o, buf, 65536, 100)
+
+
+def test_chunk_range_sharding_matches_whole():
+    # the multi-GPU split: chunk ranges processed separately concatenate to the whole result
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    buf = synth.make_buffer("stream", 2 * synth.BLOCK + 99, digit_noise=0.02)
+    n, so, ci, recs = p.find_reader_offsets(buf)
+    parts = [p.find_reader_offsets(buf, None, first, cnt) for first, cnt in ((0, 7), (7, 13), (20, -1))]
+    assert sum(x[0] for x in parts) == n
+    assert np.array_equal(np.concatenate([x[1] for x in parts]), so)
+    assert np.array_equal(np.concatenate([x[2] for x in parts]), ci)
+    assert np.array_equal(np.concatenate([x[3] for x in parts]), recs)
