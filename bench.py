@@ -173,6 +173,7 @@ def main():
     import torch.distributed as dist
     import regengo_b200 as rg
     from regengo_b200 import _lib, synth
+    from regengo_b200 import dist as rdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -189,7 +190,10 @@ def main():
     n_bytes = int(gib * (1 << 30))
     blocks = (n_bytes + synth.BLOCK - 1) // synth.BLOCK
     t0 = time.perf_counter()
-    buf = synth.make_buffer(wl["kind"], n_bytes, first_block=rank * blocks, device=dev)
+    # N > 1: ONE logical buffer of world * n_bytes, rank r holds bytes [r*n_bytes, (r+1)*n_bytes) plus a
+    # halo (the next rank's first MiB, regenerated locally from the same block generator: no exchange)
+    halo = synth.BLOCK if (world > 1 and rank < world - 1) else 0
+    buf = synth.make_buffer(wl["kind"], n_bytes + halo, first_block=rank * blocks, device=dev)
     torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
 
@@ -198,11 +202,29 @@ def main():
     d_out = torch.empty(cap_rec * nc, dtype=torch.int64, device=dev)
     d_reps = torch.empty(cap_rec, dtype=torch.int32, device=dev)
     n_rec = C.c_uint64()
+    exit_cur = C.c_int64()
+    shard_start = rank * n_bytes
+    gather_i64 = rdist.torch_all_gather_i64(device=dev) if world > 1 else None
+    exchange_rounds = [0]
 
     def step():
-        r = L.rgx_find_all_dev(ctx, pat._h, buf.data_ptr(), n_bytes, -1, d_out.data_ptr(), d_reps.data_ptr(), cap_rec, C.byref(n_rec))
-        _lib.check(r)
-        return r
+        if world == 1:
+            r = L.rgx_find_all_dev(ctx, pat._h, buf.data_ptr(), n_bytes, -1, d_out.data_ptr(), d_reps.data_ptr(), cap_rec, C.byref(n_rec))
+            _lib.check(r)
+            return r
+        # sharded: scan once, then replay the cursor until every rank's entry == its predecessor's exit
+        calls = [0]
+
+        def resolve(entry_global):
+            r = L.rgx_find_all_shard_dev(ctx, pat._h, buf.data_ptr(), n_bytes + halo, n_bytes, int(rank == world - 1),
+                                         entry_global - shard_start, shard_start, int(calls[0] > 0), d_out.data_ptr(),
+                                         d_reps.data_ptr(), cap_rec, C.byref(n_rec), C.byref(exit_cur))
+            _lib.check(r)
+            calls[0] += 1
+            return shard_start + exit_cur.value, r
+        _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64)
+        exchange_rounds[0] = rounds
+        return total_local
 
     def barrier():
         if world > 1:
@@ -232,6 +254,9 @@ def main():
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        tm = torch.tensor([int(total_matches)], dtype=torch.int64, device=dev)
+        dist.all_reduce(tm)
+        total_matches = int(tm.item())
     ms_per_step = ms_total / args.steps
     value = world * n_bytes / (ms_per_step * 1e-3) / 1e9
 
@@ -259,7 +284,8 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        assert tot == total_matches
+        if world == 1:
+            assert tot == total_matches
         e2e = {"value": world * n_bytes / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": n_bytes,
                "d2h_bytes_per_step": int(n_rec.value) * (nc * 8 + 4) + 256, "ms_per_step": dt * 1e3,
                "api": "rgx_find_all_rle (host buffers, run-length result records)"}
@@ -291,7 +317,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "bytes_per_gpu": n_bytes, "l2": "input larger than L2, no flush needed",
                        "matches_per_step": int(total_matches), "distinct_records_per_step": int(n_rec.value),
-                       "result_form": "run-length offset records left in HBM", "gen_seconds": gen_s},
+                       "result_form": "run-length offset records left in HBM", "gen_seconds": gen_s,
+                       "sharding": None if world == 1 else f"one logical buffer of {world}x{n_bytes} B, 1 MiB halo, exit-cursor all_gather (NCCL), "
+                                   f"{exchange_rounds[0]} exchange round(s); e2e is per-rank host buffers"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": sampler.result(),
         }

@@ -148,6 +148,20 @@ int64_t rgx_find_all_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf,
                          int64_t n_limit, int64_t* d_out_offsets, uint32_t* d_reps,
                          uint64_t cap_records, uint64_t* n_records);
 
+/* One shard of a logical buffer that is split over several GPUs.  d_buf holds shard_len bytes of
+ * this rank's shard followed by (buf_len - shard_len) halo bytes (the start of the next rank's
+ * shard; none on the last rank; is_last = d_buf ends where the logical input ends).  Only match starts inside the shard are reported; offsets are
+ * written as out_base + shard-relative position.  entry_cursor is where the reference's FindAll
+ * cursor stands when it reaches this shard (shard-relative; rank 0: 0; otherwise the previous rank's
+ * exit_cursor minus this shard's out_base, or a guess that is later corrected with reuse_scan=1,
+ * which re-runs only the cursor replay and the output over the cached records).  A match attempt
+ * that runs off the halo fails the call with RGX_ECAPACITY.  Only patterns on the fast TDFA scan
+ * path are supported in this version (others: RGX_EUNSUPPORTED).                                  */
+int64_t rgx_find_all_shard_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t buf_len,
+                               uint64_t shard_len, int32_t is_last, int64_t entry_cursor, int64_t out_base,
+                               int32_t reuse_scan, int64_t* d_out_offsets, uint32_t* d_reps,
+                               uint64_t cap_records, uint64_t* n_records, int64_t* exit_cursor);
+
 /* ---- FindReader: func (T) FindReader(r io.Reader, cfg stream.Config, onMatch ...) error
  *      (streaming.go:85-255) for a reader that fills every Read (bytes.Reader semantics) over
  *      `stream[0:len]`.  buffer_size/max_leftover are stream.Config{BufferSize, MaxLeftover}

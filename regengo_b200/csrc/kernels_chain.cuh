@@ -16,7 +16,7 @@ __device__ __forceinline__ uint32_t chain_step(const uint2 k, const long long se
                                                unsigned long long& nsel, unsigned long long& nreps, int* err) {
   if (k.y == KEY_INVALID) return 0;
   const long long s = seg_pos + (long long)k.x;
-  if (!(s >= cursor && (unsigned long long)cursor < len)) return 0;
+  if (!(s >= cursor && cursor < (long long)len)) return 0;   // the cursor may sit before the shard (negative)
   uint32_t reps;
   if (ENGINE == FIND_TDFA) {
     // offset += len(match) from the SLICE start (compiler.go:630-636): the record at s is returned
@@ -41,20 +41,20 @@ __device__ __forceinline__ uint32_t chain_step(const uint2 k, const long long se
 
 template <int ENGINE>
 __global__ void __launch_bounds__(64) findall_chain3_kernel(const uint64_t n_seg, const uint32_t seg_bytes, const uint32_t G,
-                                                            const uint64_t n_parts, const uint32_t mis, const uint64_t len,
+                                                            const uint64_t n_parts, const uint32_t mis, const uint64_t len_in,
                                                             const FindAllBufs fb, const Chain2Bufs cb, const int pass, int* err) {
   const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_parts) return;
   const uint64_t seg0 = p * G, seg1 = min(seg0 + G, n_seg);
   long long cursor;
-  if (p == 0) cursor = 0;
+  if (p == 0) cursor = fb.entry0;
   else if (pass == 0) cursor = (long long)(seg0 * seg_bytes) - (long long)mis;
   else cursor = cb.exit_prev[p - 1];
-  if (cursor < 0) cursor = 0;
   unsigned long long nsel = 0, nreps = 0;
   for (uint64_t seg = seg0; seg < seg1; seg++) {
     const uint32_t c = fb.count[seg];
     const long long seg_pos = (long long)(seg * seg_bytes) - (long long)mis;
+    const uint64_t len = fb.not_last ? ~0ull >> 1 : len_in;   // `offset < len(input)` refers to the whole logical input
     cb.seg_sel[seg] = (uint32_t)nsel;
     cb.seg_reps[seg] = nreps;
     const uint4* kp = reinterpret_cast<const uint4*>(fb.keys + seg * fb.K);   // fb.K is even: 16-byte aligned

@@ -33,6 +33,11 @@ struct FindAllBufs {
   int32_t* caps;       // [n_seg * K * cw] capture offsets relative to the match start
   uint32_t* reps;      // [n_seg * K] chain output: times returned (0 = skipped)
   uint32_t K, cw;      // slab capacity per segment, ints per record in caps
+  // sharding of one logical buffer over GPUs (defaults: cand_len = len, entry0 = 0, not_last = 0, out_base = 0)
+  uint64_t cand_len;   // only starts < cand_len belong to this shard (the rest of the buffer is halo)
+  long long entry0;    // cursor entering the shard (shard-relative)
+  int not_last;        // the buffer end is not the end of the logical input
+  long long out_base;  // added to every offset written by the emit kernel
 };
 
 // exact per-byte equality flags: 0x80 in every byte of x that equals the corresponding byte of pat

@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
   int32_t* M = T + nt * 32;                                                                                 // snapshot
   uint16_t* q = queue[warp];
   const uint8_t* abuf = buf - mis;
-  const uint64_t end_a = (uint64_t)mis + len;            // candidate starts are in [mis, end_a)
+  const uint64_t end_a = (uint64_t)mis + fb.cand_len;    // candidate starts are in [mis, end_a)
+  const uint64_t load_end = (uint64_t)mis + len;         // bytes exist in [mis, load_end) (shard + halo)
   const uint32_t p0 = (uint32_t)m.prefix_bytes[0] * 0x01010101u;
   const uint32_t p1 = (uint32_t)m.prefix_bytes[1] * 0x01010101u;
   const uint32_t* fast = img + m.off_t_fast;
@@ -82,11 +83,11 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
           for (int u = 0; u < FILTER_UNROLL; u++) {
             const uint64_t apos = seg_a + (uint64_t)(it0 + u) * 512 + (uint64_t)lane * 16;
             v[u] = make_uint4(0, 0, 0, 0);
-            if (apos >= mis && apos + 16 <= end_a) {
+            if (apos >= mis && apos + 16 <= load_end) {
               v[u] = *reinterpret_cast<const uint4*>(abuf + apos);
-            } else if (apos + 16 > mis && apos < end_a) {
+            } else if (apos + 16 > mis && apos < load_end) {
               uint8_t* vb = reinterpret_cast<uint8_t*>(&v[u]);
-              for (int j = 0; j < 16; j++) if (apos + j >= mis && apos + j < end_a) vb[j] = abuf[apos + j];
+              for (int j = 0; j < 16; j++) if (apos + j >= mis && apos + j < load_end) vb[j] = abuf[apos + j];
             }
           }
         }
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
               if (i < l) {
                 const uint32_t c = buf[i];
                 if (c < 128) cell = fast[state * 128 + c];
+              } else if (fb.not_last) {
+                atomicOr(err, ERR_HALO);  // a walk ran off the halo: the shard cannot decide this match alone
               }
               if ((cell & 0x3FFu) == FAST_NONE) {
                 active = false;
@@ -378,7 +381,7 @@ __global__ void findall_emit2_kernel(const DevMeta m, const uint64_t n_seg, cons
       if (keep && idx < cap_records) {
         const uint64_t rr = seg * fb.K + r;
         const uint2 k = fb.keys[rr];
-        const long long s = seg_pos + (long long)k.x, e = s + (long long)k.y;
+        const long long s0 = seg_pos + (long long)k.x, s = s0 + fb.out_base, e = s + (long long)k.y;
         int64_t* dst = out + idx * (uint64_t)nc;
         dst[0] = s; dst[1] = e;
         for (int g = 1; g < nc / 2; g++) {

@@ -1,0 +1,133 @@
+"""Multi-GPU sharding of the matching path (one process per GPU, torch.distributed for the plumbing).
+
+The three paths shard differently:
+
+  * batched MatchBytes / FindBytes -- inputs are independent: contiguous index ranges balanced by
+    bytes, no data-path collective; results are gathered with one collective (`gather_flags`).
+  * stream.FindReader              -- chunks are independent given (BufferSize, MaxLeftover): contiguous
+    chunk ranges, each rank holding its stride-aligned span plus the halo its last chunk reads.
+  * FindAllBytes over ONE buffer   -- the scan is independent per shard (plus a halo for matches that
+    start in the shard and end in the next), but the reference's cursor runs through the whole buffer,
+    so rank r needs rank r-1's exit cursor.  Every rank first replays the cursor from a guessed entry,
+    the 8-byte exit cursors are all-gathered, and ranks whose entry was wrong redo the replay (not the
+    scan) until nothing changes -- at most world_size rounds, normally two.
+
+Only the exchange logic lives here; it takes the per-rank `resolve(entry) -> (exit, payload)`
+callable as a parameter so that it can be tested on CPU with the gloo backend.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    start: int       # first byte of the shard in the logical buffer
+    shard_len: int   # bytes owned
+    buf_len: int     # bytes held (shard + halo)
+    is_last: bool
+
+
+def shard_buffer(total_len, world, rank, halo, align=1 << 20):
+    """Equal contiguous shards (multiples of `align`, remainder on the last rank) plus a halo."""
+    per = (total_len // world) // align * align
+    if per == 0:
+        per = -(-total_len // world)
+    start = min(rank * per, total_len)
+    end = total_len if rank == world - 1 else min(start + per, total_len)
+    buf_end = min(end + halo, total_len)
+    # is_last: the held bytes end at the end of the logical buffer (a walk reaching it has seen everything)
+    return Shard(rank, world, start, end - start, buf_end - start, buf_end >= total_len)
+
+
+def shard_inputs_by_bytes(offsets, world):
+    """Split inputs [0, n) into `world` contiguous index ranges with (nearly) equal byte counts.
+    offsets: uint64[n+1].  Returns a list of (first, last_exclusive)."""
+    offsets = np.asarray(offsets, dtype=np.uint64)
+    n = offsets.size - 1
+    total = int(offsets[-1] - offsets[0])
+    cuts = [0]
+    for r in range(1, world):
+        target = int(offsets[0]) + total * r // world
+        cuts.append(int(np.searchsorted(offsets, target, side="left")))
+    cuts.append(n)
+    cuts = [min(max(c, 0), n) for c in cuts]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+def shard_chunks(n_chunks, world, rank):
+    """Contiguous chunk-index range of FindReader for this rank: (first, count)."""
+    per = -(-n_chunks // world)
+    first = min(rank * per, n_chunks)
+    return first, min(per, n_chunks - first)
+
+
+def chunk_span(first, count, buffer_size, max_leftover, total_len):
+    """Stream bytes [lo, hi) that chunks first..first+count-1 read (their stride-aligned span + halo)."""
+    stride = buffer_size - max_leftover
+    if count <= 0:
+        return 0, 0
+    lo = first * stride
+    hi = min((first + count - 1) * stride + buffer_size, total_len)
+    return min(lo, total_len), hi
+
+
+def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, first_guess=None):
+    """Make every rank's entry cursor equal its predecessor's exit cursor.
+
+    resolve(entry_global) -> (exit_global, payload): replays this rank's records from `entry_global`
+    (a position in the logical buffer) and returns where the cursor leaves the shard.
+    all_gather_i64(v) -> list of every rank's v (a collective; every rank calls it the same number of
+    times).  Returns (entry, exit, payload, rounds)."""
+    entry = 0 if rank == 0 else (shard_start if first_guess is None else first_guess)
+    rounds = 0
+    exit_cur, payload = resolve(entry)
+    while True:
+        rounds += 1
+        exits = all_gather_i64(exit_cur)
+        want = 0 if rank == 0 else int(exits[rank - 1])
+        changed = int(want != entry)
+        any_changed = max(all_gather_i64(changed))
+        if not any_changed:
+            return entry, exit_cur, payload, rounds
+        if changed:
+            entry = want
+            exit_cur, payload = resolve(entry)
+        if rounds > world + 1:
+            raise RuntimeError("cursor exchange did not converge")
+
+
+def torch_all_gather_i64(group=None, device=None):
+    """all_gather of one int64 per rank with torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(v):
+        t = torch.tensor([int(v)], dtype=torch.int64, device=device)
+        out = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(out, t, group=group)
+        return [int(x.item()) for x in out]
+    return fn
+
+
+def gather_flags(local_flags, group=None, dst=0):
+    """Gather per-input result bytes (MatchBytes flags) of every rank on `dst`, in rank order."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([local_flags.numel()], dtype=torch.int64, device=local_flags.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x.item()) for x in sizes]
+    mx = max(sizes) if sizes else 0
+    padded = torch.zeros(mx, dtype=local_flags.dtype, device=local_flags.device)
+    padded[: local_flags.numel()] = local_flags
+    out = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    if dist.get_rank(group) != dst:
+        return None
+    return torch.cat([o[:s] for o, s in zip(out, sizes)])

@@ -1,0 +1,139 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 (and 3) gloo groups exercise the cursor exchange of
+sharded FindAllBytes, the byte-balanced input split and the FindReader chunk split.  The per-rank
+"device" work is played by the oracle so that the test needs no GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import compile_blob
+from oracle import Oracle
+from regengo_b200 import dist as rd
+from regengo_b200 import synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _records_for_shard(o, buf, sh):
+    """All (start, end) of matching starts inside the shard: what the device scan produces."""
+    recs = []
+    pos = sh.start
+    end = sh.start + sh.shard_len
+    while pos < end:
+        r = o.find(buf[pos: sh.start + sh.buf_len] if not sh.is_last else buf[pos:])
+        if r is None:
+            break
+        s, e = pos + r[0], pos + r[1]
+        if s >= end:
+            break
+        recs.append((s, e, r))
+        pos = s + 1
+    return recs
+
+
+def _replay_tdfa(recs, entry, total_len):
+    """The TDFA FindAll cursor rule (compiler.go:618-636) over sparse records, from `entry`."""
+    cur = entry
+    out = []
+    for s, e, r in recs:
+        if s >= cur and cur < total_len:
+            L = max(e - s, 1)
+            k = (s - cur) // L + 1
+            cur += k * L
+            out.append((s, e, k))
+    return cur, out
+
+
+def _worker(rank, world, port, total_len, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        o = Oracle(compile_blob(synth.URL_PATTERN))
+        buf = synth.make_buffer("url", total_len)
+        sh = rd.shard_buffer(total_len, world, rank, halo=4096, align=4096)
+        recs = _records_for_shard(o, buf, sh)
+        gather = rd.torch_all_gather_i64()
+        entry, exit_cur, payload, rounds = rd.resolve_cursor_chain(lambda e: _replay_tdfa(recs, e, total_len), rank, world, sh.start, gather)
+        n_local = sum(k for _, _, k in payload)
+        counts = gather(n_local)
+        q.put((rank, entry, exit_cur, n_local, [(s, e, k) for s, e, k in payload][:3], rounds, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_findall_cursor_exchange_gloo(world):
+    total_len = 6 * 65536 + 123
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total_len, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the reference result on the whole buffer
+    o = Oracle(compile_blob(synth.URL_PATTERN))
+    buf = synth.make_buffer("url", total_len)
+    n, recs = o.find_all(buf)
+    assert sum(r[3] for r in res) == n
+    assert res[0][6] == [r[3] for r in res]
+    # every rank's entry is its predecessor's exit
+    for r in range(1, world):
+        assert res[r][1] == res[r - 1][2]
+    assert res[0][1] == 0
+
+
+def test_shard_inputs_by_bytes():
+    rng = np.random.default_rng(1)
+    lens = rng.integers(0, 80, size=1000)
+    offs = np.zeros(1001, dtype=np.uint64)
+    offs[1:] = np.cumsum(lens)
+    for world in (1, 2, 3, 8):
+        parts = rd.shard_inputs_by_bytes(offs, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 1000
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [int(offs[b] - offs[a]) for a, b in parts]
+        assert max(sizes) - min(sizes) <= 160
+
+
+def test_shard_chunks_and_spans_cover_the_stream():
+    B, L, total = 65536, 1024, 1_000_000
+    stride = B - L
+    full = (total - B) // stride + 1
+    n_chunks = full + 1
+    for world in (1, 2, 4, 8):
+        seen = 0
+        for r in range(world):
+            first, cnt = rd.shard_chunks(n_chunks, world, r)
+            assert first == seen
+            seen += cnt
+            lo, hi = rd.chunk_span(first, cnt, B, L, total)
+            if cnt:
+                assert lo == first * stride and hi <= total and hi - lo <= cnt * stride + L
+        assert seen == n_chunks
+
+
+def test_shard_buffer_geometry():
+    for world in (1, 2, 4, 8):
+        total = (1 << 24) + 777
+        cover = 0
+        for r in range(world):
+            sh = rd.shard_buffer(total, world, r, halo=1 << 16)
+            assert sh.start == cover
+            cover += sh.shard_len
+            assert sh.buf_len >= sh.shard_len and sh.start + sh.buf_len <= total
+            assert sh.is_last == (sh.start + sh.buf_len == total)
+        assert cover == total

@@ -143,3 +143,46 @@ def test_unsupported_and_errors():
         p.find_all_offsets(b"123")          # no capture groups => no Find* methods (regengo.go:110)
     with pytest.raises(rg.RegengoError):
         rg.Pattern(r"(unclosed")
+
+
+def test_find_all_sharded_api_single_gpu():
+    # the multi-GPU path of bench.py, played on one GPU: three shards of one buffer scanned one after the
+    # other with rgx_find_all_shard_dev, the exit cursor of shard r fed to shard r+1
+    import ctypes as C
+    import torch
+    from regengo_b200 import _lib
+    from regengo_b200 import dist as rd
+    p, o = pair(synth.URL_PATTERN)
+    L = _lib.load()
+    ctx = rg.context(0)
+    total = 3 * synth.BLOCK + 4097
+    host = synth.make_buffer("url", total)
+    dbuf = torch.from_numpy(host).cuda()
+    nc = p.num_cap
+    cap = total // 16
+    d_out = torch.empty(cap * nc, dtype=torch.int64, device="cuda")
+    d_reps = torch.empty(cap, dtype=torch.int32, device="cuda")
+    recs, reps = [], []
+    entry = 0
+    for r in range(3):
+        sh = rd.shard_buffer(total, 3, r, halo=65536)
+        n_rec, exit_cur = C.c_uint64(), C.c_int64()
+        tot = L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                       entry - sh.start, sh.start, 0, d_out.data_ptr(), d_reps.data_ptr(), cap,
+                                       C.byref(n_rec), C.byref(exit_cur))
+        _lib.check(tot)
+        # a second call that only replays the cursor over the cached records gives the same answer
+        n_rec2, exit2 = C.c_uint64(), C.c_int64()
+        tot2 = L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                        entry - sh.start, sh.start, 1, d_out.data_ptr(), d_reps.data_ptr(), cap,
+                                        C.byref(n_rec2), C.byref(exit2))
+        assert (tot2, n_rec2.value, exit2.value) == (tot, n_rec.value, exit_cur.value)
+        torch.cuda.synchronize()
+        recs.append(d_out[: n_rec.value * nc].view(-1, nc).cpu().numpy().copy())
+        reps.append(d_reps[: n_rec.value].cpu().numpy().copy())
+        assert int(reps[-1].sum()) == tot
+        entry = sh.start + exit_cur.value
+    expanded = np.repeat(np.concatenate(recs), np.concatenate(reps).astype(np.int64), axis=0)
+    en, erecs = o.find_all(host)
+    assert expanded.shape[0] == en
+    assert np.array_equal(expanded, erecs)
