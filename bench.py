@@ -264,7 +264,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         h_in = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
-        h_in.copy_(buf)
+        h_in.copy_(buf[:n_bytes])
         h_out = torch.empty(cap_rec * nc, dtype=torch.int64, pin_memory=True)
         h_reps = torch.empty(cap_rec, dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
