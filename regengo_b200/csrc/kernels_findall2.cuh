@@ -38,8 +38,13 @@ __device__ __forceinline__ uint32_t eq_approx(uint32_t w, uint32_t pat) {
   return (x - 0x01010101u) & ~x & 0x80808080u;
 }
 
-// dynamic shared memory: [program image][tags: warps x 2 x ntags x 32 ints]
-__host__ __device__ inline size_t scan2_tag_words(int ntags) { return (size_t)SCAN2_WARPS * 2 * ntags * 32; }
+// dynamic shared memory: [program image][tags: warps x ntags x 32 ints][event logs: warps x LOG2CAP x 32 x 8 B]
+constexpr int LOG2CAP = 12;
+__host__ __device__ inline size_t scan2_tag_words(int ntags) {
+  size_t w = (size_t)SCAN2_WARPS * ntags * 32;
+  w = (w + 1) & ~(size_t)1;   // keep the uint2 log 8-byte aligned
+  return w + (size_t)SCAN2_WARPS * LOG2CAP * 32 * 2;
+}
 
 __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
     const DevMeta m, const uint32_t* __restrict__ gimg, const uint8_t* __restrict__ buf, const uint64_t len,
@@ -52,8 +57,9 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nt = m.t_ntags;
-  int32_t* T = reinterpret_cast<int32_t*>(smem_all + m.image_words) + (size_t)warp * 2 * nt * 32 + lane;  // live tags: T[j*32]
-  int32_t* M = T + nt * 32;                                                                                 // snapshot
+  int32_t* T = reinterpret_cast<int32_t*>(smem_all + m.image_words) + (size_t)warp * nt * 32 + lane;      // tags: T[j*32]
+  uint2* LG = reinterpret_cast<uint2*>(reinterpret_cast<int32_t*>(smem_all + m.image_words) + (size_t)SCAN2_WARPS * nt * 32) +
+              (size_t)warp * LOG2CAP * 32 + lane;                                                         // event log: LG[e*32]
   uint16_t* q = queue[warp];
   const uint8_t* abuf = buf - mis;
   const uint64_t end_a = (uint64_t)mis + fb.cand_len;    // candidate starts are in [mis, end_a)
@@ -146,20 +152,22 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
           bool active = k < n;
           const uint32_t srel = active ? q[k] : 0;
           const int64_t s = (int64_t)(seg_a + srel) - (int64_t)mis;
-          // tags are positions relative to the candidate start; -1 = unset
-          for (int j = 0; j < nt; j++) T[j * 32] = -1;
-          T[0] = 0;
-          for (int t = 0; t < m.t_n_init_any; t++) T[img[m.off_t_init + m.t_n_init_begin + t] * 32] = 0;
+          // WALK: state transitions only.  Tag lists that fire are appended to a per-lane event log
+          // {list id, position}; accept lists are logged lazily (when the list changes).  The tags are
+          // rebuilt from the log afterwards, with all lanes converged.
           int64_t i = s;
           uint32_t state = (uint32_t)m.t_start_any;
           int32_t match_end = -1;   // relative to s
-          uint32_t pend_al = 0;     // accept tag list waiting to be applied at position match_end
-          bool snap = false;        // M[] holds the tags of the last accept (else T[] does)
+          uint32_t pend_al = 0;     // accept tag list in force at match_end
+          uint32_t nlog = 0;
+          uint32_t word = 0;        // the aligned 4 input bytes that contain byte i
+          bool have = false;
           while (__any_sync(0xFFFFFFFFu, active)) {
             if (active) {
               uint32_t cell = FAST_NONE;
               if (i < l) {
-                const uint32_t c = buf[i];
+                if (!have || ((i + mis) & 3) == 0) { word = *reinterpret_cast<const uint32_t*>(abuf + (((uint64_t)(i + mis)) & ~3ull)); have = true; }
+                const uint32_t c = (word >> ((uint32_t)((i + mis) & 3) * 8)) & 255u;
                 if (c < 128) cell = fast[state * 128 + c];
               } else if (fb.not_last) {
                 atomicOr(err, ERR_HALO);  // a walk ran off the halo: the shard cannot decide this match alone
@@ -170,45 +178,52 @@ __global__ void __launch_bounds__(SCAN2_WARPS * 32, 3) findall_scan_tdfa_kernel(
                 const int32_t pos = (int32_t)(i + 1 - s);  // tag value base: i + 1 - start
                 const uint32_t al = (cell >> 10) & 0x3FFu;
                 if (al) {
-                  // a transition list may touch the same tags: flush the lazy accept list first
-                  if (pend_al) {
-                    for (uint32_t a = aoff[pend_al]; a < aoff[pend_al + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = match_end - (int32_t)(x >> 16); }
-                    pend_al = 0;
-                  }
-                  if (match_end >= 0 && !snap) {
-                    for (int j = 0; j < nt; j++) M[j * 32] = T[j * 32];
-                    snap = true;
-                  }
-                  for (uint32_t a = aoff[al]; a < aoff[al + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = pos - (int32_t)(x >> 16); }
+                  if (pend_al) { if (nlog < LOG2CAP) LG[nlog * 32] = make_uint2(pend_al, (uint32_t)match_end); nlog++; pend_al = 0; }
+                  if (nlog < LOG2CAP) LG[nlog * 32] = make_uint2(al, (uint32_t)pos);
+                  nlog++;
                 }
                 state = cell & 0x3FFu;
                 if ((cell >> 30) && ((cell & (1u << 30)) || i == l - 1)) {
                   const uint32_t aal = (cell >> 20) & 0x3FFu;
                   if (aal != pend_al) {
-                    if (pend_al)
-                      for (uint32_t a = aoff[pend_al]; a < aoff[pend_al + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = match_end - (int32_t)(x >> 16); }
+                    if (pend_al) { if (nlog < LOG2CAP) LG[nlog * 32] = make_uint2(pend_al, (uint32_t)match_end); nlog++; }
                     pend_al = aal;
                   }
                   match_end = pos;
-                  snap = false;
                 }
                 i++;
               }
             }
           }
-          // publish candidate k (all lanes converged here)
+          if (nlog > LOG2CAP) atomicOr(err, ERR_DENSE);   // more tag events than the log holds: generic scan instead
+          // REPLAY: tags := -1; apply, in order, every logged list whose position is <= match_end (events
+          // after the last accept never reached the snapshot, tdfa.go:963-975), then the accept list in force.
+          for (int j = 0; j < nt; j++) T[j * 32] = -1;
+          T[0] = 0;
+          for (int t = 0; t < m.t_n_init_any; t++) T[img[m.off_t_init + m.t_n_init_begin + t] * 32] = 0;
+          const bool matched = k < n && match_end >= 0;
+          uint32_t nmax = matched ? min(nlog, (uint32_t)LOG2CAP) : 0;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xFFFFFFFFu, nmax, o));
+          const uint32_t nmine = matched ? min(nlog, (uint32_t)LOG2CAP) : 0;
+          for (uint32_t e = 0; e < nmax; e++) {
+            if (e < nmine) {
+              const uint2 ev = LG[e * 32];
+              if ((int32_t)ev.y <= match_end)
+                for (uint32_t a = aoff[ev.x]; a < aoff[ev.x + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = (int32_t)ev.y - (int32_t)(x >> 16); }
+            }
+          }
+          if (matched && pend_al)
+            for (uint32_t a = aoff[pend_al]; a < aoff[pend_al + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = match_end - (int32_t)(x >> 16); }
+          // publish candidate k
           if (k < n) {
             const uint64_t r = seg * fb.K + slot_base + k;
             if (slot_base + k < fb.K) {
               if (match_end >= 0) {
-                const int32_t* src = T;
-                if (snap) src = M;
-                else if (pend_al)
-                  for (uint32_t a = aoff[pend_al]; a < aoff[pend_al + 1]; a++) { const uint32_t x = alist[a]; T[(x & 0xFFFFu) * 32] = match_end - (int32_t)(x >> 16); }
                 fb.keys[r] = make_uint2(srel, (uint32_t)match_end);
                 for (int j = 2; j < nt; j += 2) {
-                  const int32_t a = src[j * 32];
-                  int32_t b = src[(j + 1) * 32];
+                  const int32_t a = T[j * 32];
+                  int32_t b = T[(j + 1) * 32];
                   if (a >= 0 && b < 0) b = match_end;  // unset group end := match end (tdfa.go:1039-1041)
                   fb.caps[r * fb.cw + (j - 2)] = a;
                   fb.caps[r * fb.cw + (j - 1)] = b;
