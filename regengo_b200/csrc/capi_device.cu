@@ -17,6 +17,8 @@
 #include "kernels_findall2.cuh"
 #include "kernels_chain.cuh"
 #include "kernels_scan4.cuh"
+#include "kernels_emit.cuh"
+#include "kernels_btrun.cuh"
 #include "kernels_stream.cuh"
 
 using namespace rgx;
@@ -41,6 +43,7 @@ struct rgx_ctx {
   void* h_small = nullptr;  // pinned, 4 KiB
   uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
   uint32_t fa_stack_cap = 256;
+  int chain_first_batch = 8;  // chain passes queued before the first readback (adapts to the data)
   // optional per-phase timing of the last FindAll (CUDA events on the launching stream)
   bool timing = false;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};

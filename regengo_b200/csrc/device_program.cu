@@ -207,6 +207,47 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
   else if (!first.all()) m.gen_kind = GEN_BYTESET;
   else m.gen_kind = GEN_ALL;
   m.image_words = (uint32_t)w.size();
+
+  // Recognise  (cap|nop)* C+ (cap|nop)* b ...  (greedy loop over an ASCII class C, then a literal byte
+  // b outside C).  An attempt at s then succeeds iff the maximal C-run from s is followed by b and the
+  // rest matches after it -- the same outcome for every s of the run (kernels_btrun.cuh has the proof).
+  if (P.find_engine == FIND_BT && !P.anchored && !P.find_memo) {
+    std::vector<int> indeg(n, 0);
+    for (uint32_t i = 0; i < n; i++) {
+      const Inst& in = prog.inst[i];
+      if (in.op == InstFail || in.op == InstMatch) continue;
+      indeg[in.out]++;
+      if (in.op == InstAlt || in.op == InstAltMatch) indeg[in.arg]++;
+    }
+    int pc = prog.start;
+    uint32_t start_caps = 1u;  // captures[0] = searchStart
+    bool ok = true;
+    size_t guard = 0;
+    while (ok && guard++ <= n && (prog.inst[pc].op == InstCapture || prog.inst[pc].op == InstNop)) {
+      if (prog.inst[pc].op == InstCapture) { if (prog.inst[pc].arg < 32) start_caps |= 1u << prog.inst[pc].arg; else ok = false; }
+      if (pc != prog.start && indeg[pc] != 1) ok = false;
+      pc = (int)prog.inst[pc].out;
+    }
+    const int L = pc;
+    ok = ok && prog.inst[L].op == InstRune && !P.unicode_class[L] && indeg[L] == (L == prog.start ? 1 : 2);
+    int A = ok ? (int)prog.inst[L].out : 0;
+    ok = ok && prog.inst[A].op == InstAlt && (int)prog.inst[A].out == L && indeg[A] == 1 && A != L;
+    if (ok) {
+      pc = (int)prog.inst[A].arg;
+      guard = 0;
+      while (ok && guard++ <= n && (prog.inst[pc].op == InstCapture || prog.inst[pc].op == InstNop)) {
+        if (indeg[pc] != 1) ok = false;
+        pc = (int)prog.inst[pc].out;
+      }
+      const Inst& lit = prog.inst[pc];
+      ok = ok && lit.op == InstRune1 && lit.rune.size() == 1 && lit.rune[0] < 128 && indeg[pc] == 1;
+      if (ok) {
+        const uint32_t b = (uint32_t)lit.rune[0];
+        if ((P.class_bits[(size_t)L * 8 + (b >> 5)] >> (b & 31)) & 1u) ok = false;   // b must not be in C
+        if (ok) { m.run_ok = 1; m.run_class_pc = L; m.run_lit = (int32_t)b; m.run_start_caps = start_caps; }
+      }
+    }
+  }
 }
 
 }  // namespace rgx

@@ -41,6 +41,12 @@ struct DevMeta {
   int32_t nullable;            // a match attempt can succeed without consuming input
   int32_t n_alt;               // number of Alt instructions (stack sizing)
   int32_t n_capinst;
+  // "leading class loop + literal" start filter of the backtracking FindAll scan (kernels_btrun.cuh):
+  // the program is  (cap|nop)* C+ (cap|nop)* b ...  with b a byte outside the class C
+  int32_t run_ok;              // shape recognised
+  int32_t run_class_pc;        // the Rune instruction of C (its 256-bit set is at off_cls + 8*pc)
+  int32_t run_lit;             // b
+  uint32_t run_start_caps;     // capture slots written before the loop (they hold the attempt's start)
 };
 
 struct DeviceImage {

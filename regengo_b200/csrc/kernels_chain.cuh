@@ -14,12 +14,27 @@ constexpr int CHAIN_PF = 4;   // 16-byte loads in flight per lane
 
 // One record of the replay.  `cursor` is relative to the part's first byte (it may be far negative
 // when it enters the shard from a predecessor).
+constexpr int FIND_BT_RUN = 3;   // backtracking records that stand for a whole run of starts (kernels_btrun.cuh)
+
 template <int ENGINE>
 __device__ __forceinline__ uint32_t chain_step(const uint2 k, const long long seg_rel, const long long len_rel, long long& cursor,
                                                uint32_t& nsel, unsigned long long& nreps, int* err) {
+  if (k.y == KEY_INVALID) return 0;
+  if (ENGINE == FIND_BT_RUN) {
+    // key = {first (signed, segment-relative), len << 12 | (last - first)}: every start in [first, last]
+    // matches and ends at first + len.  The reference takes the smallest matching start >= cursor and
+    // moves the cursor to the match end (find.go:452-457).
+    const long long first = seg_rel + (long long)(int32_t)k.x;
+    const long long last = first + (long long)(k.y & 0xFFFu);
+    if (!(last >= cursor && cursor < len_rel)) return 0;
+    const long long s = cursor > first ? cursor : first;
+    cursor = first + (long long)(k.y >> 12);
+    nsel++;
+    nreps++;
+    return 1u + (uint32_t)(s - first);
+  }
   const long long s = seg_rel + (long long)k.x;
-  const bool take = k.y != KEY_INVALID && s >= cursor && cursor < len_rel;
-  if (!take) return 0;
+  if (!(s >= cursor && cursor < len_rel)) return 0;
   uint32_t reps;
   if (ENGINE == FIND_TDFA) {
     // offset += len(match) from the SLICE start (compiler.go:630-636): the record at s is returned
@@ -161,3 +176,4 @@ __global__ void __launch_bounds__(1024) findall_part_scan2_kernel(const uint64_t
 }
 
 }  // namespace rgx
+

@@ -186,3 +186,24 @@ def test_find_all_sharded_api_single_gpu():
     en, erecs = o.find_all(host)
     assert expanded.shape[0] == en
     assert np.array_equal(expanded, erecs)
+
+
+def test_find_all_run_anchor_path():
+    # backtracking patterns of the shape C+ b rest take the run-anchor scan (kernels_btrun.cuh)
+    cases = [
+        (r"(\w+)@(\w)", [b"a@bc@d", b"ab@cd@ef@g", b"@a@b", b"x@", b"aaaa@bbbb@cccc@d" * 30]),
+        (synth.EMAIL_PATTERN, [b"a@b.c@d.e", b"user@host.com,other@x.yz;", b"a..b@c.d", b"x@y.z@w.v name@host @ a@.b a@b."]),
+        (r"(?P<k>[a-z]+)=(?P<v>\d*);", [b"abc=12;de=;f=3", b"k=v;kk=1;", b"=1;a=2;"]),
+        (r"([a-c]+)-(x|[a-c]+-y)", [b"abc-x abc-abc-y ab-ab-x", b"a-a-a-a-y"]),
+    ]
+    for pat, inputs in cases:
+        p, o = pair(pat)
+        for b in inputs:
+            check_find_all(p, o, b)
+            check_find_all(p, o, (b + b" ") * 600)        # crosses 8 KiB segments and 64 KiB parts
+            check_find_all(p, o, b * 3, n=2)
+    # a run longer than a segment, and one longer than the 4095-byte record field (generic scan fallback)
+    p, o = pair(synth.EMAIL_PATTERN)
+    check_find_all(p, o, b"x" * 3000 + b"@host.com " + b"y" * 9000 + b"@h.io " + b"z" * 100 + b"@q.rs")
+    buf = synth.make_buffer("log", 2 * synth.BLOCK)
+    check_find_all(p, o, buf[5:])                        # unaligned device pointer
