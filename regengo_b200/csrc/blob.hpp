@@ -39,7 +39,8 @@ enum BlobFlags : uint32_t {
 };
 
 // per-instruction flag bits (byte 1 of inst word 0)
-enum InstFlags : uint32_t { IF_ALT_CKPT = 1, IF_GREEDY_LOOP = 2, IF_UNICODE_CLASS = 4, IF_CHAR_STATE = 8 };
+enum InstFlags : uint32_t { IF_ALT_CKPT = 1, IF_GREEDY_LOOP = 2, IF_UNICODE_CLASS = 4, IF_CHAR_STATE = 8,
+                            IF_ATOMIC_LOOP = 16 /* device image only, see device_program.cu */ };
 
 // TDFA section header (word offsets relative to H_OFF_TDFA)
 enum TdfaHdr : int {

@@ -206,6 +206,33 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
   else if (m.prefix_len > 0) m.gen_kind = GEN_PREFIX;
   else if (!first.all()) m.gen_kind = GEN_BYTESET;
   else m.gen_kind = GEN_ALL;
+  // "Atomic" greedy loops: an Alt A whose body is one ASCII class instruction C looping straight back to
+  // A, and whose exit (reached only from A) leads through captures/nops to a literal byte b outside C.
+  // Of the alternatives the reference stacks for such a loop only the NEWEST is the loop's exit; the older
+  // ones (shorter run lengths) resume at a byte of C and die at once on b.  A FindAll attempt -- where only
+  // success, end and captures of the successful path are observable -- therefore keeps one stack entry
+  // per loop and overwrites it each iteration (engines.cuh, MODE_FINDALL without memoisation).
+  std::vector<int> indeg_all(n, 0);
+  for (uint32_t i = 0; i < n; i++) {
+    const Inst& in = prog.inst[i];
+    if (in.op == InstFail || in.op == InstMatch) continue;
+    indeg_all[in.out]++;
+    if (in.op == InstAlt || in.op == InstAltMatch) indeg_all[in.arg]++;
+  }
+  for (uint32_t i = 0; i < n; i++) {
+    const Inst& a = prog.inst[i];
+    if (a.op != InstAlt || indeg_all[a.arg] != 1) continue;
+    const uint32_t L = a.out;
+    if (L >= n || prog.inst[L].op != InstRune || P.unicode_class[L] || prog.inst[L].out != i) continue;
+    uint32_t pc = a.arg;
+    size_t guard = 0;
+    while (guard++ <= n && (prog.inst[pc].op == InstCapture || prog.inst[pc].op == InstNop)) pc = prog.inst[pc].out;
+    const Inst& lit = prog.inst[pc];
+    if (lit.op != InstRune1 || lit.rune.size() != 1 || lit.rune[0] >= 128) continue;
+    const uint32_t b = (uint32_t)lit.rune[0];
+    if ((P.class_bits[(size_t)L * 8 + (b >> 5)] >> (b & 31)) & 1u) continue;
+    w[m.off_inst + 4 * i] |= (uint32_t)IF_ATOMIC_LOOP << 8;
+  }
   m.image_words = (uint32_t)w.size();
 
   // Recognise  (cap|nop)* C+ (cap|nop)* b ...  (greedy loop over an ASCII class C, then a literal byte
@@ -244,7 +271,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       if (ok) {
         const uint32_t b = (uint32_t)lit.rune[0];
         if ((P.class_bits[(size_t)L * 8 + (b >> 5)] >> (b & 31)) & 1u) ok = false;   // b must not be in C
-        if (ok) { m.run_ok = 1; m.run_class_pc = L; m.run_lit = (int32_t)b; m.run_start_caps = start_caps; }
+        if (ok) { m.run_ok = 1; m.run_class_pc = L; m.run_lit = (int32_t)b; m.run_start_caps = start_caps; m.run_resume_pc = (int)prog.inst[A].arg; }
       }
     }
   }

@@ -47,6 +47,7 @@ struct DevMeta {
   int32_t run_class_pc;        // the Rune instruction of C (its 256-bit set is at off_cls + 8*pc)
   int32_t run_lit;             // b
   uint32_t run_start_caps;     // capture slots written before the loop (they hold the attempt's start)
+  int32_t run_resume_pc;       // instruction after the loop (the Alt's exit): attempts of a run resume here at offset p
 };
 
 struct DeviceImage {

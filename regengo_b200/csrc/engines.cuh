@@ -84,7 +84,8 @@ __device__ __forceinline__ void clear_visited(const Scratch& sc) {
 // Returns 1 on Match.  MODE_FINDALL: one attempt at searchStart (0 => "searchStart++").
 template <int MODE>
 __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* __restrict__ in, int64_t l,
-                          int64_t search_start, int32_t* caps, const Scratch& sc, int* err) {
+                          int64_t search_start, int32_t* caps, const Scratch& sc, int* err, int resume_pc = -1,
+                          int64_t resume_off = 0, uint32_t resume_start_caps = 0) {
   const int ncap = m.num_cap;
   const bool anchored = (m.flags & F_ANCHORED) != 0;
   const bool needs_bt = (m.flags & F_NEEDS_BT) != 0;
@@ -113,6 +114,13 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
     caps[0] = 0;
   }
   pc = m.start;
+  if (MODE == MODE_FINDALL && resume_pc >= 0) {
+    // resume an attempt after its leading class loop (kernels_btrun.cuh): the captures written before
+    // the loop hold the attempt's start, the stack is empty (the loop's alternatives cannot succeed)
+    pc = resume_pc;
+    offset = resume_off;
+    for (int i = 0; i < ncap; i++) if ((resume_start_caps >> i) & 1u) caps[i] = 0;
+  }
 
   for (;;) {
     const uint4 I = insts[pc];
@@ -215,6 +223,17 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
           uint32_t* vp = &sc.visited[(size_t)word * sc.stride + sc.tid];
           if (*vp & bit) { fail = true; break; }
           *vp |= bit;
+        }
+        if (MODE == MODE_FINDALL && !memo && (ifl & IF_ATOMIC_LOOP) && sp > 0) {
+          // Atomic loop (device_program.cu): the alternative stacked by the previous iteration (same exit,
+          // one byte earlier, same captures) can only fail, so it is replaced instead of kept.
+          uint2* top = &sc.stack[(size_t)(sp - 1) * sc.stride + sc.tid];
+          const uint2 e = *top;
+          if ((e.y & 0xFFFFu) == I.z && (int64_t)e.x + 1 == offset - base) {
+            top->x = (uint32_t)(offset - base);
+            pc = (int)I.y;
+            break;
+          }
         }
         if (sp >= sc.stack_cap) { atomicOr(err, ERR_STACK); return 0; }
         const int64_t rel = offset - base;

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
         int32_t caps[MAX_CAPS];
         const uint64_t r = seg * fb.K + k;
         uint2 key = make_uint2(0, KEY_INVALID);
-        if (bt_machine<MODE_FINDALL>(m, img, buf, (int64_t)len, s0, caps, sc, err)) {
+        if (bt_machine<MODE_FINDALL>(m, img, buf, (int64_t)len, s0, caps, sc, err, m.run_resume_pc, p, m.run_start_caps)) {
           const int64_t first_rel = s0 - ((int64_t)seg_a - (int64_t)mis);   // may be negative: the run began in an earlier segment
           const int64_t run_extra = p - 1 - s0;
           const int64_t mlen = caps[1];
