@@ -149,54 +149,57 @@ __global__ void __launch_bounds__(SCAN4_WARPS * 32, 4) findall_scan4_kernel(
     // bytes readable from segp, as a 32-bit limit (a walk longer than 4 GiB is out of range)
     const uint64_t avail64 = load_end - seg_a;
     const uint32_t lim = avail64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)avail64;
-    const bool lim_is_end = avail64 <= 0xFFFFFFF0ull;
+    const uint32_t lim_eot = avail64 <= 0xFFFFFFF0ull ? lim : 0xFFFFFFFFu;   // ri value that means "the buffer's last byte was just consumed"
     const uint32_t n = tail;
+    const uint32_t fast_s = smem_u32(fast);   // shared-window address of the cell table (row = 128 cells = 512 B)
     for (uint32_t base = 0; base < n; base += 32) {
       const uint32_t k = base + lane;
-      bool active = k < n;
+      uint32_t active = k < n ? 1u : 0u;
       const uint32_t srel = active ? q[k] : 0;
       uint32_t ri = srel;                      // next byte to read, relative to segp
-      uint32_t state_sh = (uint32_t)m.t_start_any << 7;
-      int32_t match_end = -1;                  // relative to the candidate start
+      uint32_t row = fast_s + ((uint32_t)m.t_start_any << 9);
+      uint32_t acc_ri = 0;                     // ri just after the last accepting step (0: none yet; ri >= 1 there)
       uint32_t pend_al = 0, nlog = 0;
-      bool hit_end = false, log_ovf = false;
+      uint32_t wflags = 0;                     // 1: ran into the end of the buffer, 2: event log overflow
       uint32_t word = 0;
       if (active) {
-        if (ri >= lim) { active = false; hit_end = true; }
+        if (ri >= lim) { active = 0; wflags = 1; }
         else word = *reinterpret_cast<const uint32_t*>(segp + (ri & ~3u)) >> ((ri & 3u) * 8);
       }
       while (__any_sync(0xFFFFFFFFu, active)) {
-#pragma unroll
-        for (int rep = 0; rep < 2; rep++) {
-          if (active) {
-            const uint32_t c = word & 255u;
-            const uint32_t cell = c < 128 ? fast[state_sh + c] : FAST_NONE;
-            if ((cell & 0x3FFu) == FAST_NONE) {
-              active = false;
-            } else {
-              ri++;
-              if (cell & 0x000FFC00u) {  // a transition tag list fires at position ri - srel
-                const uint32_t pos = ri - srel;
-                if (pend_al) { if (nlog < LOG4CAP) LG[nlog * 32] = (pend_al << 22) | (uint32_t)match_end; nlog++; pend_al = 0; }
-                if (nlog < LOG4CAP) LG[nlog * 32] = (((cell >> 10) & 0x3FFu) << 22) | pos;
-                nlog++;
-                if (pos >= (1u << 22)) log_ovf = true;
-              }
-              state_sh = (cell & 0x3FFu) << 7;
-              if ((cell >> 30) && ((cell & (1u << 30)) || (lim_is_end && ri == lim))) {
+        if (active) {
+          const uint32_t c = word & 255u;
+          uint32_t cell = FAST_NONE;
+          if (c < 128) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cell) : "r"(row + c * 4u));
+          if ((cell & 0x3FFu) == FAST_NONE) {
+            active = 0;
+          } else {
+            ri++;
+            if (__builtin_expect((cell & 0x000FFC00u) != 0, 0)) {  // a transition tag list fires at position ri - srel
+              const uint32_t pos = ri - srel;
+              if (pend_al) { if (nlog < LOG4CAP) LG[nlog * 32] = (pend_al << 22) | (acc_ri - srel); nlog++; pend_al = 0; }
+              if (nlog < LOG4CAP) LG[nlog * 32] = (((cell >> 10) & 0x3FFu) << 22) | pos;
+              nlog++;
+              if (pos >= (1u << 22)) wflags |= 2u;
+            }
+            row = fast_s + ((cell & 0x3FFu) << 9);
+            if (cell & 0xC0000000u) {
+              if ((cell & 0x40000000u) || ri == lim_eot) {
                 const uint32_t aal = (cell >> 20) & 0x3FFu;
-                if (aal != pend_al) {
-                  if (pend_al) { if (nlog < LOG4CAP) LG[nlog * 32] = (pend_al << 22) | (uint32_t)match_end; nlog++; }
+                if (__builtin_expect(aal != pend_al, 0)) {
+                  if (pend_al) { if (nlog < LOG4CAP) LG[nlog * 32] = (pend_al << 22) | (acc_ri - srel); nlog++; }
                   pend_al = aal;
                 }
-                match_end = (int32_t)(ri - srel);
+                acc_ri = ri;
               }
-              if (ri >= lim) { active = false; hit_end = true; }
-              else { word >>= 8; if ((ri & 3u) == 0) word = *reinterpret_cast<const uint32_t*>(segp + ri); }
             }
+            if (ri >= lim) { active = 0; wflags |= 1u; }
+            else { word >>= 8; if ((ri & 3u) == 0) word = *reinterpret_cast<const uint32_t*>(segp + ri); }
           }
         }
       }
+      const int32_t match_end = acc_ri ? (int32_t)(acc_ri - srel) : -1;   // relative to the candidate start
+      const bool hit_end = (wflags & 1u) != 0, log_ovf = (wflags & 2u) != 0;
       if (hit_end && fb.not_last) atomicOr(err, ERR_HALO);   // ran off the halo: this shard cannot decide the match alone
       if (nlog > LOG4CAP || log_ovf || match_end >= (1 << 22)) atomicOr(err, ERR_DENSE);  // generic scan instead
       // REPLAY
