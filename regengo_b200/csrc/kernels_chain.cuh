@@ -177,3 +177,4 @@ __global__ void __launch_bounds__(1024) findall_part_scan2_kernel(const uint64_t
 
 }  // namespace rgx
 
+
