@@ -16,7 +16,7 @@
 #include "kernels_findall.cuh"
 #include "kernels_findall2.cuh"
 #include "kernels_chain.cuh"
-#include "kernels_scan4.cuh"
+#include "kernels_scan5.cuh"
 #include "kernels_emit.cuh"
 #include "kernels_btrun.cuh"
 #include "kernels_stream.cuh"

@@ -181,12 +181,49 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     nullable = t.accept[t.start_any] || t.accept_eot[t.start_any];
     for (uint32_t c = 0; c < 128; c++) if (t.trans[(size_t)t.start_any * 128 + c] >= 0) first.set(c);
     int s = t.start_any;
+    std::vector<int> prefix_states{s};   // prefix_states[i] = state after i prefix bytes
+    std::vector<uint32_t> prefix_lists;  // transition list fired by prefix byte i
     while (m.prefix_len < MAX_PREFIX && !t.accept[s] && !t.accept_eot[s]) {
       int only = -1, cnt = 0;
       for (int c = 0; c < 128; c++) if (t.trans[(size_t)s * 128 + c] >= 0) { only = c; cnt++; }
       if (cnt != 1) break;
       m.prefix_bytes[m.prefix_len++] = (uint8_t)only;
+      prefix_lists.push_back(list_id(t.actions[(size_t)s * 128 + only]));
       s = t.trans[(size_t)s * 128 + only];
+      prefix_states.push_back(s);
+    }
+    if (m.off_t_fast) {
+      // walks may skip the verified prefix up to the last state that does not accept
+      int skip = m.prefix_len;
+      while (skip > 0 && (t.accept[prefix_states[skip]] || t.accept_eot[prefix_states[skip]])) skip--;
+      m.t_skip_len = skip;
+      m.t_skip_state = prefix_states[skip];
+      for (int i = 0; i < skip; i++)
+        if (prefix_lists[i]) m.t_pre_ev[m.t_pre_n++] = (prefix_lists[i] << 22) | (uint32_t)(i + 1);
+      // per state: the "boring" cell (same state, no transition list), identical for every byte that has it
+      m.off_t_selftab = (uint32_t)w.size();
+      for (int st = 0; st < t.num_states; st++) {
+        uint32_t self = 0xFFFFFFFFu;
+        for (int c = 0; c < 128; c++) {
+          const uint32_t cell = w[m.off_t_fast + (size_t)st * 128 + c];
+          if ((cell & 0x3FFu) == (uint32_t)st && ((cell >> 10) & 0x3FFu) == 0) self = cell;
+        }
+        w.push_back(self);
+      }
+      align4();
+      // action lists flattened for the replay, 2 words per list: word0 = a0 | a1 << 16, word1 = a2 | n << 16 |
+      // generic << 24 with a = tag:8 | offset:8.  Lists with more than 3 actions or fields above 255 set
+      // `generic` and are replayed from the list arrays.
+      m.off_t_adesc = (uint32_t)w.size();
+      for (auto& l : lists) {
+        bool simple = l.size() <= 3;
+        for (uint32_t x : l) if ((x >> 16) > 255 || (x & 0xFFFFu) > 255) simple = false;
+        uint32_t a[3] = {0, 0, 0};
+        if (simple) for (size_t i = 0; i < l.size(); i++) a[i] = (l[i] & 0xFFu) | (((l[i] >> 16) & 0xFFu) << 8);
+        w.push_back(a[0] | (a[1] << 16));
+        w.push_back(a[2] | ((simple ? (uint32_t)l.size() : 0u) << 16) | ((simple ? 0u : 1u) << 24));
+      }
+      align4();
     }
   } else {
     first_bytes_bt(P, first, nullable);

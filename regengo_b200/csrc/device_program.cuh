@@ -33,6 +33,13 @@ struct DevMeta {
   uint32_t off_t_trans, off_t_accept, off_t_alist_off, off_t_alist, off_t_init, off_first;
   // "fast" TDFA cells (0 = absent): next:10 | transition alist:10 | accept alist of NEXT:10 | next accepts:1 | next accepts at EOT:1
   uint32_t off_t_fast;
+  // scan5 extras (0 = absent): per state, the cell that stays in the state without tag actions (or ~0u);
+  // per action list, a 64-bit descriptor {n:8 | (tag:8, offset:8) x 3} chained by list id (see pack_program)
+  uint32_t off_t_selftab, off_t_adesc;
+  // walks of verified candidates start after `t_skip_len` prefix bytes, in state `t_skip_state`, with
+  // `t_pre_n` tag events already logged (every state on the way is non-accepting)
+  int32_t t_skip_len, t_skip_state, t_pre_n;
+  uint32_t t_pre_ev[8];
   int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
   uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;
   // FindAll candidate generator (start filter); see findall_kernels.cu
