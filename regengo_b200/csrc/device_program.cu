@@ -194,7 +194,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     }
     if (m.off_t_fast) {
       // walks may skip the verified prefix up to the last state that does not accept
-      int skip = m.prefix_len;
+      int skip = m.prefix_len < 4 ? m.prefix_len : 4;   // the filter compares at most 4 prefix bytes
       while (skip > 0 && (t.accept[prefix_states[skip]] || t.accept_eot[prefix_states[skip]])) skip--;
       m.t_skip_len = skip;
       m.t_skip_state = prefix_states[skip];

@@ -4,11 +4,12 @@
 // scan4 was issue-bound (0.83 warp instructions per input byte, profiles/r1_b_ncu_scan4_c3.txt); this
 // version cuts the instruction count of both halves:
 //
-//   FILTER  a lane owns 64 contiguous bytes of every 2 KiB block (four 16-byte loads, the next block's
-//           loads in flight while this one is compared).  Per word: z = (w ^ p0) | (w>>8 ^ p1) has a zero
-//           byte exactly where the two pattern bytes start (5 ALU ops, false positives allowed); hits
-//           are rare, so only the OR of the 16 flag words is computed unconditionally.  Lanes with hits
-//           pack their flags into two words, a warp prefix sum hands out ordered queue slots.
+//   FILTER  a lane owns 64 contiguous bytes of every 2 KiB block (four 16-byte loads plus the word that
+//           follows, issued right after the previous block was compared).  Per word
+//           z = (w ^ p0) | (w>>8 ^ p1) | (w>>16 ^ p2) | (w>>24 ^ p3) has a zero byte exactly where the
+//           first PLEN <= 4 bytes of the literal prefix start (exact zero-byte test), so every queued
+//           candidate is a verified prefix occurrence and its walk starts behind it.  Flags are packed
+//           into two words per lane; a warp prefix sum hands out ordered queue slots.
 //   WALK    as soon as 32 candidates are queued (the bytes are still in L1/L2), one TDFA walk per lane in
 //           two alternating phases:
 //             A  skip "boring" bytes -- cells that stay in the same state without tag actions, recognised
@@ -31,7 +32,6 @@ namespace rgx {
 
 constexpr int SCAN5_WARPS = 8;
 constexpr uint32_t BLK5 = 2048;          // bytes per filter block (64 per lane)
-constexpr uint32_t QV_UNVERIFIED = 0x8000u;   // queue entry flag: the literal prefix was not compared by the filter
 constexpr uint32_t NOSELF = 0xFFFFFFFFu;
 
 __host__ __device__ inline size_t scan5_extra_words(int ntags) {
@@ -44,7 +44,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   return v;
 }
 
-__global__ void __launch_bounds__(SCAN5_WARPS * 32, 3) findall_scan5_kernel(
+template <int PLEN>
+__global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
     const DevMeta m, const uint32_t* __restrict__ gimg, const uint8_t* __restrict__ buf, const uint64_t len,
     const uint32_t mis, const uint64_t n_seg, const FindAllBufs fb, int* err) {
   extern __shared__ __align__(16) uint32_t smem_all[];
@@ -63,19 +64,19 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 3) findall_scan5_kernel(
   const uint64_t load_end = (uint64_t)mis + len;          // bytes exist in [mis, load_end) (shard + halo)
   const uint32_t p0 = (uint32_t)m.prefix_bytes[0] * 0x01010101u;
   const uint32_t p1 = (uint32_t)m.prefix_bytes[1] * 0x01010101u;
+  const uint32_t p2 = (uint32_t)m.prefix_bytes[2] * 0x01010101u;
+  const uint32_t p3 = (uint32_t)m.prefix_bytes[3] * 0x01010101u;
   const uint32_t* fast = img + m.off_t_fast;
   const uint32_t* aoff = img + m.off_t_alist_off;
   const uint32_t* alist = img + m.off_t_alist;
   const uint64_t total_warps = (uint64_t)gridDim.x * SCAN5_WARPS;
   constexpr uint32_t N_BLK = SEG2_BYTES / BLK5;
   const uint32_t fast_s = smem_u32(fast);   // shared-window address of the cell table (row = 128 cells = 512 B)
-  const uint32_t start_row = fast_s + ((uint32_t)m.t_start_any << 9);
   const uint32_t selftab_s = smem_u32(img + m.off_t_selftab);
   const uint32_t* adesc = img + m.off_t_adesc;
   const uint32_t skip_len = (uint32_t)m.t_skip_len;
   const uint32_t skip_row = fast_s + ((uint32_t)m.t_skip_state << 9);
   const uint32_t skip_self = img[m.off_t_selftab + m.t_skip_state];
-  const int plen = m.prefix_len;
 
   for (uint64_t seg = (uint64_t)blockIdx.x * SCAN5_WARPS + warp; seg < n_seg; seg += total_warps) {
     const uint64_t seg_a = seg * SEG2_BYTES;
@@ -89,26 +90,21 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 3) findall_scan5_kernel(
     const uint32_t lim_eot = avail64 <= 0xFFFFFFF0ull ? lim : 0xFFFFFFFFu;   // ri value that means "the buffer's last byte was just consumed"
 
     // ---------------- WALK / REPLAY / PUBLISH of queue entries [base, min(base + 32, n)) ----------------
-    // Queue entry = segment-relative start | QV_UNVERIFIED.  Verified entries (the whole literal prefix was
-    // compared by the filter) begin after t_skip_len bytes in t_skip_state with the prefix's tag events
-    // pre-logged; the few unverified ones (too close to the end of the buffer) walk from the start state.
+    // Queue entry = segment-relative start of a verified prefix occurrence: the walk begins after
+    // t_skip_len <= PLEN bytes in t_skip_state with the tag events of those transitions pre-logged.
     auto walk_batch = [&](const uint32_t base, const uint32_t n) {
       const uint32_t k = base + lane;
       uint32_t active = k < n ? 1u : 0u;
-      const uint32_t qe = active ? q[k] : 0;
-      const uint32_t srel = qe & 0x7FFFu;
-      const bool verified = !(qe & QV_UNVERIFIED);
-      uint32_t ri = srel + (verified ? skip_len : 0u);     // next byte to read, relative to segp
-      uint32_t row = verified ? skip_row : start_row;
-      uint32_t selfcell = verified ? skip_self : NOSELF;   // the cell that keeps this state and fires nothing
+      const uint32_t srel = active ? q[k] : 0;
+      uint32_t ri = srel + skip_len;           // next byte to read, relative to segp
+      uint32_t row = skip_row;
+      uint32_t selfcell = skip_self;           // the cell that keeps this state and fires nothing (NOSELF: none)
       uint32_t cur_acc = 0;                    // the current state accepts (not only at end of text)
       uint32_t acc_ri = 0;                     // ri just after the last accepting step (0: none yet; ri >= 1 there)
-      uint32_t pend_al = 0, nlog = 0;
+      uint32_t pend_al = 0;
       uint32_t wflags = 0;                     // 1: ran into the end of the buffer, 2: event log overflow
-      if (verified) {
-        for (int e = 0; e < m.t_pre_n; e++) LG[e * 32] = m.t_pre_ev[e];
-        nlog = (uint32_t)m.t_pre_n;
-      }
+      for (int e = 0; e < m.t_pre_n; e++) LG[e * 32] = m.t_pre_ev[e];
+      uint32_t nlog = (uint32_t)m.t_pre_n;
       // Lanes in a state without a boring cell step (phase B) until every live lane sits in a looping
       // state; then all of them skip their boring runs together (phase A) and take one step out.
       bool exit_step = false;
@@ -235,65 +231,66 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 3) findall_scan5_kernel(
     };
 
     // ---------------- FILTER ----------------
-    auto load16 = [&](uint32_t blk, int u) -> uint4 {
-      const uint64_t apos = seg_a + (uint64_t)blk * BLK5 + (uint64_t)lane * 64 + (uint64_t)u * 16;
-      if (interior || (apos >= mis && apos + 16 <= load_end)) return *reinterpret_cast<const uint4*>(abuf + apos);
+    // bytes outside [mis, load_end) read as 0 and never start a candidate: a prefix cut off by the end of
+    // the buffer cannot match (every prefix state is non-accepting)
+    const bool interior_ld = interior && seg_a + SEG2_BYTES + 4 <= load_end;
+    auto load_guarded = [&](const uint64_t apos, const int nb) -> uint4 {
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (apos + 16 > mis && apos < load_end) {
+      if (apos + nb > mis && apos < load_end) {
         uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
-        for (int j = 0; j < 16; j++) if (apos + j >= mis && apos + j < load_end) vb[j] = abuf[apos + j];
+        for (int j = 0; j < nb; j++) if (apos + j >= mis && apos + j < load_end) vb[j] = abuf[apos + j];
       }
       return v;
     };
-    uint4 nxt[4];
+    uint32_t w[17];
+    auto load_block = [&](const uint32_t blk) {
+      const uint32_t off = blk * BLK5 + lane * 64;
+      if (interior_ld) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) nxt[u] = load16(0, u);
-    for (uint32_t blk = 0; blk < N_BLK; blk++) {
-      uint32_t w[17];
+        for (int u = 0; u < 4; u++) {
+          const uint4 v = *reinterpret_cast<const uint4*>(segp + off + u * 16);
+          w[4 * u] = v.x; w[4 * u + 1] = v.y; w[4 * u + 2] = v.z; w[4 * u + 3] = v.w;
+        }
+        w[16] = *reinterpret_cast<const uint32_t*>(segp + off + 64);
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; u++) { w[4 * u] = nxt[u].x; w[4 * u + 1] = nxt[u].y; w[4 * u + 2] = nxt[u].z; w[4 * u + 3] = nxt[u].w; }
-      if (blk + 1 < N_BLK) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) nxt[u] = load16(blk + 1, u);
+        for (int u = 0; u < 4; u++) {
+          const uint64_t apos = seg_a + off + u * 16;
+          const uint4 v = (apos >= mis && apos + 16 <= load_end) ? *reinterpret_cast<const uint4*>(abuf + apos) : load_guarded(apos, 16);
+          w[4 * u] = v.x; w[4 * u + 1] = v.y; w[4 * u + 2] = v.z; w[4 * u + 3] = v.w;
+        }
+        w[16] = load_guarded(seg_a + off + 64, 4).x;
       }
-      // the byte after this lane's 64 is the next lane's first; the last lane cannot see its successor and
-      // keeps its 64th byte as a candidate on the first pattern byte alone
-      w[16] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
-      if (lane == 31) w[16] = p1;
+    };
+    load_block(0);
+    for (uint32_t blk = 0; blk < N_BLK; blk++) {
       // flags -> two words, bit 8*byte + word (word 0..7): 32 bytes each
       uint32_t e0 = 0, e1 = 0;
 #pragma unroll
       for (int j = 0; j < 16; j++) {
-        const uint32_t z = (w[j] ^ p0) | (__funnelshift_r(w[j], w[j + 1], 8) ^ p1);
-        const uint32_t d = (z - 0x01010101u) & ~z & 0x80808080u;
+        uint32_t z = (w[j] ^ p0) | (__funnelshift_r(w[j], w[j + 1], 8) ^ p1);
+        if (PLEN > 2) z |= __funnelshift_r(w[j], w[j + 1], 16) ^ p2;
+        if (PLEN > 3) z |= __funnelshift_r(w[j], w[j + 1], 24) ^ p3;
+        const uint32_t d = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);   // 0x80 exactly in the zero bytes
         if (j < 8) e0 |= d >> (7 - j); else e1 |= d >> (15 - j);
       }
-      if (__ballot_sync(0xFFFFFFFFu, (e0 | e1) != 0)) {
-        uint32_t unver = 0;   // bit i: this lane's i-th hit (in bit order over e0 then e1) could not be verified
-        if (e0 | e1) {
-          // keep a hit only if it lies in the candidate range and the whole literal prefix is there
-          const uint64_t apos = seg_a + (uint64_t)blk * BLK5 + (uint64_t)lane * 64;
-          uint32_t nk = 0;
-          for (int half = 0; half < 2; half++) {
-            uint32_t e = half ? e1 : e0, keep = 0;
-            while (e) {
-              const uint32_t b = __ffs(e) - 1;
-              e &= e - 1;
-              const uint64_t ap = apos + half * 32 + 4 * (b & 7u) + (b >> 3);
-              bool ok = interior || (ap >= mis && ap < end_a);
-              if (ok) {
-                if (ap + plen <= load_end) {
-                  for (int t = 0; ok && t < plen; t++) ok = abuf[ap + t] == m.prefix_bytes[t];
-                } else {
-                  unver |= 1u << nk;   // the walk decides (and reports a halo overrun on a shard)
-                }
-              }
-              if (ok) { keep |= 1u << b; nk++; }
-            }
-            if (half) e1 = keep; else e0 = keep;
+      if (blk + 1 < N_BLK) load_block(blk + 1);
+      if (!interior && (e0 | e1)) {
+        // clip to the candidate range [mis, end_a)
+        const uint64_t apos = seg_a + (uint64_t)blk * BLK5 + (uint64_t)lane * 64;
+        for (int half = 0; half < 2; half++) {
+          uint32_t e = half ? e1 : e0, keep = 0;
+          while (e) {
+            const uint32_t b = __ffs(e) - 1;
+            e &= e - 1;
+            const uint64_t ap = apos + half * 32 + 4 * (b & 7u) + (b >> 3);
+            if (ap >= mis && ap < end_a) keep |= 1u << b;
           }
+          if (half) e1 = keep; else e0 = keep;
         }
-        const uint32_t c = __popc(e0) + __popc(e1);
+      }
+      const uint32_t c = __popc(e0) + __popc(e1);
+      if (__ballot_sync(0xFFFFFFFFu, c != 0)) {
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
@@ -301,19 +298,17 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 3) findall_scan5_kernel(
         if (c) {
           // this lane's hits, inserted in position order (the packed flags are byte-major)
           const uint32_t wb = tail + incl - c;
-          const uint32_t pbase = blk * BLK5 + lane * 64;
-          uint32_t i = 0;
-          for (int half = 0; half < 2; half++) {
-            uint32_t e = half ? e1 : e0;
-            while (e) {
-              const uint32_t b = __ffs(e) - 1;
-              e &= e - 1;
-              const uint32_t pos = pbase + half * 32 + 4 * (b & 7u) + (b >> 3);
-              uint32_t j = i;
-              while (j > 0 && wb + j - 1 < Q4CAP && (q[wb + j - 1] & 0x7FFFu) > pos) { if (wb + j < Q4CAP) q[wb + j] = q[wb + j - 1]; j--; }
-              if (wb + j < Q4CAP) q[wb + j] = (uint16_t)(pos | (((unver >> i) & 1u) ? QV_UNVERIFIED : 0u));
-              i++;
-            }
+          uint32_t pbase = blk * BLK5 + lane * 64;
+          uint32_t i = 0, e = e0;
+          for (;;) {
+            if (!e) { if (!e1) break; e = e1; e1 = 0; pbase += 32; }
+            const uint32_t b = __ffs(e) - 1;
+            e &= e - 1;
+            const uint32_t pos = pbase + 4 * (b & 7u) + (b >> 3);
+            uint32_t j = i;
+            while (j > 0 && wb + j - 1 < Q4CAP && q[wb + j - 1] > pos) { if (wb + j < Q4CAP) q[wb + j] = q[wb + j - 1]; j--; }
+            if (wb + j < Q4CAP) q[wb + j] = (uint16_t)pos;
+            i++;
           }
         }
         tail += total;

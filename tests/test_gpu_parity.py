@@ -207,3 +207,35 @@ def test_find_all_run_anchor_path():
     check_find_all(p, o, b"x" * 3000 + b"@host.com " + b"y" * 9000 + b"@h.io " + b"z" * 100 + b"@q.rs")
     buf = synth.make_buffer("log", 2 * synth.BLOCK)
     check_find_all(p, o, buf[5:])                        # unaligned device pointer
+
+
+@pytest.mark.parametrize("pattern,lit", [
+    (r"(?P<k>ab)(?P<v>[\w.]+)(?::(?P<n>\d+))?", b"ab"),          # 2-byte literal prefix
+    (r"(?P<k>key)=(?P<v>[\w.]+)(?:;(?P<n>\d+))?", b"key="),      # prefix longer than 3, first 4 bytes compared
+    (r"(?P<k>id:)(?P<v>\w+)(?:/(?P<n>\d+))?", b"id:"),           # 3-byte literal prefix
+    (synth.URL_PATTERN, b"http"),
+])
+def test_fast_scan_prefix_boundaries(pattern, lit):
+    """The fast TDFA scan compares the first <= 4 bytes of the literal prefix 64 bytes per lane, 2 KiB per
+    block, 32 KiB per segment: put occurrences (and near misses) across every one of those boundaries and
+    at both ends of the buffer, at every alignment of the device pointer the API can produce."""
+    p, o = pair(pattern, force_tdfa=True)
+    assert p.info.find_engine == 2
+    tail = {b"ab": b"x.y:77", b"key=": b"v.1;5", b"id:": b"w9/31", b"http": b"://h.io:8/p"}[lit]
+    rng = np.random.default_rng(7)
+    n = 3 * 32768 + 700
+    buf = bytearray(rng.choice(np.frombuffer(b"abkeyid:=htp xyz\n", dtype=np.uint8), size=n).tobytes())
+    tok = lit + tail
+    for edge in (64, 128, 2048, 4096, 32768, 65536, 98304):
+        for d in range(-len(tok) - 1, 3):
+            pos = edge + d
+            if 0 <= pos and pos + 1 <= n and rng.integers(0, 2):
+                buf[pos:pos + len(tok)] = tok[: n - pos]
+    buf[:len(tok)] = tok
+    buf[n - len(lit):] = lit                       # a prefix cut off by the end of the buffer
+    check_find_all(p, o, bytes(buf))
+    check_find_all(p, o, bytes(buf[: n - 1]))
+    check_find_all(p, o, bytes(buf[5: 40000]))
+    check_find_all(p, o, lit)
+    check_find_all(p, o, tok)
+    check_find_all(p, o, (tok + b" ") * 3000)       # dense: every lane has several hits
