@@ -39,7 +39,7 @@ struct rgx_ctx {
   int64_t launches = 0;
   // grow-only scratch
   DevBuf stack, cstack, visited, small, in_bytes, in_offs, out_flag, out_rec, out_reps, out_aux;
-  DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase, ch_segsel, ch_segreps, ch_entry;
+  DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase, ch_segsel, ch_segreps, ch_entry, ch_tile;
   void* h_small = nullptr;  // pinned, 4 KiB
   uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
   uint32_t fa_stack_cap = 256;
@@ -225,7 +225,7 @@ void rgx_ctx_destroy(rgx_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->stack, &c->cstack, &c->visited, &c->small, &c->in_bytes, &c->in_offs, &c->out_flag, &c->out_rec,
                     &c->out_reps, &c->out_aux, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
-                    &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase, &c->ch_segsel, &c->ch_segreps, &c->ch_entry};
+                    &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase, &c->ch_segsel, &c->ch_segreps, &c->ch_entry, &c->ch_tile};
   for (DevBuf* b : bufs) free_buf(*b);
   if (c->h_small) cudaFreeHost(c->h_small);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);

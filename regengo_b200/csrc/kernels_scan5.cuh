@@ -33,6 +33,7 @@ namespace rgx {
 constexpr int SCAN5_WARPS = 8;
 constexpr uint32_t BLK5 = 2048;          // bytes per filter block (64 per lane)
 constexpr uint32_t NOSELF = 0xFFFFFFFFu;
+constexpr uint32_t NOCELL = 0xFFFFFFFEu;   // no cell value has transition list 0x3FF and next state 0x3FE
 
 __host__ __device__ inline size_t scan5_extra_words(int ntags) {
   return (size_t)SCAN5_WARPS * ntags * 32 + (size_t)SCAN5_WARPS * (LOG4CAP + 1) * 32;
@@ -108,17 +109,19 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
       // Lanes in a state without a boring cell step (phase B) until every live lane sits in a looping
       // state; then all of them skip their boring runs together (phase A) and take one step out.
       bool exit_step = false;
+      uint32_t pre_cell = NOCELL;
       for (;;) {
         const bool do_b = active && (exit_step || selfcell == NOSELF);
         if (!__any_sync(0xFFFFFFFFu, do_b)) {
           if (!__any_sync(0xFFFFFFFFu, active)) break;
-          // phase A: boring bytes, four per iteration
+          // phase A: boring bytes, four per iteration; the cell that ends the run is handed to phase B
           if (active) {
             uint32_t a = ri & ~3u;
-            if (a + 12 <= lim) {
+            if (a + 16 <= lim) {
               const uint32_t sh = (ri & 3u) * 8u;
               uint32_t lo = *reinterpret_cast<const uint32_t*>(segp + a);
               uint32_t hi = *reinterpret_cast<const uint32_t*>(segp + a + 4);
+              uint32_t hi2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
               for (;;) {
                 const uint32_t w = __funnelshift_r(lo, hi, sh);
                 if (w & 0x80808080u) break;
@@ -126,14 +129,14 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
                 const uint32_t c1 = lds_u32(row + ((w >> 6) & 0x3FCu));
                 const uint32_t c2 = lds_u32(row + ((w >> 14) & 0x3FCu));
                 const uint32_t c3 = lds_u32(row + ((w >> 22) & 0x3FCu));
-                if (c0 != selfcell) break;
-                if (c1 != selfcell) { ri += 1; break; }
-                if (c2 != selfcell) { ri += 2; break; }
-                if (c3 != selfcell) { ri += 3; break; }
+                if (c0 != selfcell) { pre_cell = c0; break; }
+                if (c1 != selfcell) { pre_cell = c1; ri += 1; break; }
+                if (c2 != selfcell) { pre_cell = c2; ri += 2; break; }
+                if (c3 != selfcell) { pre_cell = c3; ri += 3; break; }
                 ri += 4; a += 4;
-                if (a + 12 > lim) break;
-                lo = hi;
-                hi = *reinterpret_cast<const uint32_t*>(segp + a + 4);
+                if (a + 16 > lim) break;
+                lo = hi; hi = hi2;
+                hi2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
               }
             }
           }
@@ -146,9 +149,13 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
           if (cur_acc) acc_ri = ri;            // the accepting state looped up to here
           if (ri >= lim) { active = 0; wflags |= 1u; }
           else {
-            const uint32_t c = segp[ri];
-            uint32_t cell = FAST_NONE;
-            if (c < 128) cell = lds_u32(row + c * 4u);
+            uint32_t cell = pre_cell;            // phase A already looked the byte at ri up (ri < lim there)
+            pre_cell = NOCELL;
+            if (cell == NOCELL) {
+              const uint32_t c = segp[ri];
+              cell = FAST_NONE;
+              if (c < 128) cell = lds_u32(row + c * 4u);
+            }
             if ((cell & 0x3FFu) == FAST_NONE) {
               active = 0;
             } else {
@@ -264,15 +271,28 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
     };
     load_block(0);
     for (uint32_t blk = 0; blk < N_BLK; blk++) {
-      // flags -> two words, bit 8*byte + word (word 0..7): 32 bytes each
+      // flags -> two words, bit 8*byte + word (word 0..7): 32 bytes each.  The cheap zero-byte test can
+      // only err on the byte right above a true zero byte, i.e. when two hits touch; that (practically
+      // never) redoes the block with the exact test.
       uint32_t e0 = 0, e1 = 0;
 #pragma unroll
       for (int j = 0; j < 16; j++) {
         uint32_t z = (w[j] ^ p0) | (__funnelshift_r(w[j], w[j + 1], 8) ^ p1);
         if (PLEN > 2) z |= __funnelshift_r(w[j], w[j + 1], 16) ^ p2;
         if (PLEN > 3) z |= __funnelshift_r(w[j], w[j + 1], 24) ^ p3;
-        const uint32_t d = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);   // 0x80 exactly in the zero bytes
+        const uint32_t d = (z - 0x01010101u) & ~z & 0x80808080u;
         if (j < 8) e0 |= d >> (7 - j); else e1 |= d >> (15 - j);
+      }
+      if ((e0 & (e0 >> 8)) | (e1 & (e1 >> 8))) {
+        e0 = 0; e1 = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          uint32_t z = (w[j] ^ p0) | (__funnelshift_r(w[j], w[j + 1], 8) ^ p1);
+          if (PLEN > 2) z |= __funnelshift_r(w[j], w[j + 1], 16) ^ p2;
+          if (PLEN > 3) z |= __funnelshift_r(w[j], w[j + 1], 24) ^ p3;
+          const uint32_t d = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);   // 0x80 exactly in the zero bytes
+          if (j < 8) e0 |= d >> (7 - j); else e1 |= d >> (15 - j);
+        }
       }
       if (blk + 1 < N_BLK) load_block(blk + 1);
       if (!interior && (e0 | e1)) {
