@@ -215,14 +215,24 @@ def main():
         # sharded: scan once, then replay the cursor until every rank's entry == its predecessor's exit
         calls = [0]
 
-        def resolve(entry_global):
+        def shard_call(entry_global, mode):
             r = L.rgx_find_all_shard_dev(ctx, pat._h, buf.data_ptr(), n_bytes + halo, n_bytes, int(rank == world - 1),
-                                         entry_global - shard_start, shard_start, int(calls[0] > 0), d_out.data_ptr(),
+                                         entry_global - shard_start, shard_start, mode, d_out.data_ptr(),
                                          d_reps.data_ptr(), cap_rec, C.byref(n_rec), C.byref(exit_cur))
             _lib.check(r)
+            return r
+        last_entry = [0]
+
+        def resolve(entry_global):
+            # mode bit 1: cursor replay only; bit 0: the scan of this step is already cached
+            shard_call(entry_global, 2 | int(calls[0] > 0))
             calls[0] += 1
-            return shard_start + exit_cur.value, r
-        _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64)
+            last_entry[0] = entry_global
+            return shard_start + exit_cur.value, None
+
+        def finish():
+            return shard_call(last_entry[0], 4)   # output only
+        _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64, finish=finish)
         exchange_rounds[0] = rounds
         return total_local
 

@@ -97,6 +97,10 @@ int rgx_ctx_create(int32_t device, rgx_ctx** out);
 void rgx_ctx_destroy(rgx_ctx* c);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 int64_t rgx_ctx_launches(const rgx_ctx* c);
+/* Upload granularity of the host-buffer FindAll (rgx_find_all / rgx_find_all_rle): inputs of at least two
+ * chunks are uploaded chunk by chunk while earlier chunks are scanned (default 256 MiB; a multiple of
+ * 32 KiB, at least 64 KiB). */
+int rgx_ctx_set_chunk_bytes(rgx_ctx* c, uint64_t bytes);
 /* Per-phase device timing of the last rgx_find_all*_dev call (CUDA events recorded on the context's
  * stream): out_ms[4] = {scan kernel, chain kernels, compaction kernels, all three}. */
 int rgx_ctx_enable_timing(rgx_ctx* c, int32_t on);
@@ -153,8 +157,12 @@ int64_t rgx_find_all_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf,
  * shard; none on the last rank; is_last = d_buf ends where the logical input ends).  Only match starts inside the shard are reported; offsets are
  * written as out_base + shard-relative position.  entry_cursor is where the reference's FindAll
  * cursor stands when it reaches this shard (shard-relative; rank 0: 0; otherwise the previous rank's
- * exit_cursor minus this shard's out_base, or a guess that is later corrected with reuse_scan=1,
- * which re-runs only the cursor replay and the output over the cached records).  A match attempt
+ * exit_cursor minus this shard's out_base, or a guess that is corrected later).  reuse_scan is a
+ * bit set: 1 = the records of the previous call on this context are reused (no scan), 2 = replay
+ * the cursor only (no output; *n_records = 0, *exit_cursor valid), 4 = output only, from the records
+ * and the replay of the previous call.  A multi-GPU caller scans and replays with 2, all-gathers the
+ * exit cursors, replays again with 2|1 where its entry was wrong, and ends with 4
+ * (regengo_b200/dist.py).  A match attempt
  * that runs off the halo fails the call with RGX_ECAPACITY.  Only patterns on the fast TDFA scan
  * path are supported in this version (others: RGX_EUNSUPPORTED).                                  */
 int64_t rgx_find_all_shard_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t buf_len,

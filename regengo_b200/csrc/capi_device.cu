@@ -35,6 +35,9 @@ struct DevBuf {
 struct rgx_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;   // host-buffer FindAll: input upload / result download overlap the kernels
+  uint64_t chunk_bytes = 256ull << 20;                         // upload granularity of the pipelined host-buffer FindAll
+  std::vector<cudaEvent_t> chunk_ev;                           // one "uploaded" event per input chunk
   int sm_count = 0;
   int64_t launches = 0;
   // grow-only scratch
@@ -211,6 +214,8 @@ int rgx_ctx_create(int32_t device, rgx_ctx** out) {
     return RGX_ECUDA;
   }
   CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
   CU(cudaMallocHost(&c->h_small, 4096));
   int rc = ensure(c, c->small, 4096);
   if (rc) { delete c; return rc; }
@@ -229,11 +234,20 @@ void rgx_ctx_destroy(rgx_ctx* c) {
   for (DevBuf* b : bufs) free_buf(*b);
   if (c->h_small) cudaFreeHost(c->h_small);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->chunk_ev) if (e) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 int64_t rgx_ctx_launches(const rgx_ctx* c) { return c ? c->launches : 0; }
+
+int rgx_ctx_set_chunk_bytes(rgx_ctx* c, uint64_t bytes) {
+  if (!c || bytes < (1u << 16) || (bytes & 0x7FFFu)) { set_error("rgx_ctx_set_chunk_bytes: need a multiple of 32 KiB, at least 64 KiB"); return RGX_EINVAL; }
+  c->chunk_bytes = bytes;
+  return RGX_OK;
+}
 
 int rgx_ctx_enable_timing(rgx_ctx* c, int32_t on) {
   if (!c) return RGX_EINVAL;

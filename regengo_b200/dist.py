@@ -76,11 +76,13 @@ def chunk_span(first, count, buffer_size, max_leftover, total_len):
     return min(lo, total_len), hi
 
 
-def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, first_guess=None):
+def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, first_guess=None, finish=None):
     """Make every rank's entry cursor equal its predecessor's exit cursor.
 
     resolve(entry_global) -> (exit_global, payload): replays this rank's records from `entry_global`
     (a position in the logical buffer) and returns where the cursor leaves the shard.
+    finish() -> payload (optional): when given, `resolve` only replays the cursor and `finish` produces
+    the output once, after the entries have settled (saves the output pass of every discarded round).
     all_gather_i64(v) -> list of every rank's v (a collective; every rank calls it the same number of
     times).  Returns (entry, exit, payload, rounds)."""
     entry = 0 if rank == 0 else (shard_start if first_guess is None else first_guess)
@@ -93,6 +95,8 @@ def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, firs
         changed = int(want != entry)
         any_changed = max(all_gather_i64(changed))
         if not any_changed:
+            if finish is not None:
+                payload = finish()
             return entry, exit_cur, payload, rounds
         if changed:
             entry = want

@@ -177,6 +177,18 @@ def test_find_all_sharded_api_single_gpu():
                                         entry - sh.start, sh.start, 1, d_out.data_ptr(), d_reps.data_ptr(), cap,
                                         C.byref(n_rec2), C.byref(exit2))
         assert (tot2, n_rec2.value, exit2.value) == (tot, n_rec.value, exit_cur.value)
+        # the multi-GPU exchange: replay from a wrong guess without output (mode 2|1), replay from the true
+        # entry (2|1), then output only (4) -- same records, same exit
+        wrong = C.c_int64()
+        _lib.check(L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                            0, sh.start, 3, d_out.data_ptr(), d_reps.data_ptr(), cap, C.byref(n_rec2), C.byref(wrong)))
+        _lib.check(L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                            entry - sh.start, sh.start, 3, d_out.data_ptr(), d_reps.data_ptr(), cap, C.byref(n_rec2), C.byref(exit2)))
+        assert n_rec2.value == 0 and exit2.value == exit_cur.value
+        d_out.zero_(); d_reps.zero_()
+        tot3 = L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                        entry - sh.start, sh.start, 4, d_out.data_ptr(), d_reps.data_ptr(), cap, C.byref(n_rec2), C.byref(exit2))
+        assert (tot3, n_rec2.value, exit2.value) == (tot, n_rec.value, exit_cur.value)
         torch.cuda.synchronize()
         recs.append(d_out[: n_rec.value * nc].view(-1, nc).cpu().numpy().copy())
         reps.append(d_reps[: n_rec.value].cpu().numpy().copy())
@@ -239,3 +251,28 @@ def test_fast_scan_prefix_boundaries(pattern, lit):
     check_find_all(p, o, lit)
     check_find_all(p, o, tok)
     check_find_all(p, o, (tok + b" ") * 3000)       # dense: every lane has several hits
+
+
+def test_find_all_host_buffer_pipelined_upload():
+    """rgx_find_all over a host buffer uploads the input in chunks and scans chunk i as a shard of the buffer
+    while chunk i+1 is in flight (entry cursor = previous exit, halo = next chunk).  With 64 KiB chunks a
+    3.3 MiB buffer takes 53 chunks; URLs straddle many chunk boundaries."""
+    from regengo_b200 import _lib
+    p, o = pair(synth.URL_PATTERN)
+    L = _lib.load()
+    ctx = rg.context(0)
+    _lib.check(L.rgx_ctx_set_chunk_bytes(ctx, 1 << 16))
+    try:
+        buf = bytearray(synth.make_buffer("url", 3 * synth.BLOCK + 300001).tobytes())
+        u = b"https://ab.example.com:8080/p/q"
+        for k in range(1, 40):
+            pos = k * 65536 - (k % len(u))
+            buf[pos:pos + len(u)] = u
+        check_find_all(p, o, bytes(buf))
+        check_find_all(p, o, bytes(buf[: 2 * 65536]))
+        check_find_all(p, o, bytes(buf[: 2 * 65536 + 1]))
+        # the email pattern is not on the sharded path: the call must take the one-shot route and agree
+        p2, o2 = pair(synth.EMAIL_PATTERN)
+        check_find_all(p2, o2, synth.make_buffer("log", synth.BLOCK + 17))
+    finally:
+        _lib.check(L.rgx_ctx_set_chunk_bytes(ctx, 256 << 20))
