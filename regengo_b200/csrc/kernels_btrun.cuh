@@ -17,13 +17,13 @@
 //   chain (kernels_chain.cuh, FIND_BT_RUN) then takes max(cursor, first) as the reference does when its
 //   cursor lands inside a run, and the emit kernel substitutes that start into the start-valued captures.
 //
-// One warp per 8 KiB segment; a record belongs to the segment that holds its b.
+// One warp per 32 KiB segment; a record belongs to the segment that holds its b.
 #pragma once
 #include "kernels_findall2.cuh"
 
 namespace rgx {
 
-constexpr uint32_t SEGB_BYTES = 8192;
+constexpr uint32_t SEGB_BYTES = 32768;   // ~80 candidates per segment on log text: 2-3 nearly full verify batches
 constexpr uint32_t QBCAP = 1024;
 constexpr int BTRUN_WARPS = 8;
 
