@@ -206,6 +206,8 @@ def main():
     shard_start = rank * n_bytes
     gather_i64 = rdist.torch_all_gather_i64(device=dev) if world > 1 else None
     exchange_rounds = [0]
+    phase = (C.c_float * 4)()
+    step_phase = [0.0, 0.0, 0.0]   # scan, chain, emit of the current step (sharded path: summed over its calls)
 
     def step():
         if world == 1:
@@ -226,12 +228,20 @@ def main():
         def resolve(entry_global):
             # mode bit 1: cursor replay only; bit 0: the scan of this step is already cached
             shard_call(entry_global, 2 | int(calls[0] > 0))
+            L.rgx_ctx_last_timing(ctx, phase)
+            if calls[0] == 0:
+                step_phase[0], step_phase[1] = phase[0], phase[1]
+            else:
+                step_phase[1] += phase[1]      # a corrected replay
             calls[0] += 1
             last_entry[0] = entry_global
             return shard_start + exit_cur.value, None
 
         def finish():
-            return shard_call(last_entry[0], 4)   # output only
+            r = shard_call(last_entry[0], 4)      # output only
+            L.rgx_ctx_last_timing(ctx, phase)
+            step_phase[2] = phase[2]
+            return r
         _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64, finish=finish)
         exchange_rounds[0] = rounds
         return total_local
@@ -249,12 +259,14 @@ def main():
     launches0 = rg.launches(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
-    phase = (C.c_float * 4)()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
-        L.rgx_ctx_last_timing(ctx, phase)
-        scan_ms.append((phase[0], phase[1], phase[2]))
+        if world == 1:
+            L.rgx_ctx_last_timing(ctx, phase)
+            scan_ms.append((phase[0], phase[1], phase[2]))
+        else:
+            scan_ms.append(tuple(step_phase))
     ev1.record(stream)
     barrier()
     sampler.stop_flag = True
@@ -312,7 +324,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "kernel": "findall_scan_kernel", "peak_source": peak_src, "scan_ms": scan,
+                    "kernel": "findall_scan5_kernel<4>" if args.workload == "c3" else "findall_scan_btrun_kernel", "peak_source": peak_src, "scan_ms": scan,
                     "chain_ms": float(np.mean([s[1] for s in scan_ms])), "emit_ms": float(np.mean([s[2] for s in scan_ms])),
                     "algorithmic_bytes_per_launch": n_bytes}
         cpu = None
