@@ -266,6 +266,62 @@ __device__ __forceinline__ long long chain_replay_part_tdfa32(const uint64_t p, 
   return (long long)c + part_pos;
 }
 
+// The same replay by a whole WARP, for the short worklist passes whose cost is one part's latency: lanes load
+// 32 keys at once (coalesced) and prepare start / length / reciprocal in parallel; the cursor chain itself runs
+// redundantly in every lane over shuffled operands (about 12 issue slots per record instead of ~35 dependent
+// ones), and lane j keeps record j's result so that the repeat counts are stored coalesced.
+__device__ __forceinline__ long long chain_replay_part_tdfa32_warp(const uint64_t p, const long long entry, const uint64_t n_seg,
+                                                                   const uint32_t seg_bytes, const uint32_t G, const uint32_t mis,
+                                                                   const uint64_t len_in, const FindAllBufs& fb, const Chain4Bufs& cb) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t seg0 = p * G, seg1 = min(seg0 + G, n_seg);
+  const long long part_pos = (long long)(seg0 * seg_bytes) - (long long)mis;
+  const long long len_rel = fb.not_last ? (long long)(~0ull >> 2) : (long long)len_in - part_pos;
+  const int32_t len32 = len_rel > 0x7FFFFFFFll ? 0x7FFFFFFF : (int32_t)len_rel;
+  int32_t c = (int32_t)(entry - part_pos);
+  uint32_t nsel = 0;
+  unsigned long long nreps = 0;
+  for (uint64_t seg = seg0; seg < seg1; seg++) {
+    const uint32_t cnt = fb.count[seg];
+    const int32_t seg_rel = (int32_t)((seg - seg0) * seg_bytes);
+    if (lane == 0) { cb.seg_sel[seg] = nsel; cb.seg_reps[seg] = nreps; }
+    const uint2* kp = fb.keys + seg * fb.K;
+    uint32_t* rp = fb.reps + seg * fb.K;
+    uint2 nxt = (uint32_t)lane < cnt ? kp[lane] : make_uint2(0, KEY_INVALID);
+    for (uint32_t base = 0; base < cnt; base += 32) {
+      const uint2 k = nxt;
+      if (base + 32 < cnt) nxt = base + 32 + lane < cnt ? kp[base + 32 + lane] : make_uint2(0, KEY_INVALID);
+      const int32_t my_s = seg_rel + (int32_t)k.x;
+      const uint32_t my_valid = k.y != KEY_INVALID ? 1u : 0u;
+      const uint32_t my_L = (k.y && my_valid) ? k.y : 1u;
+      const uint32_t my_M = __float2uint_rz(__fdividef(4294967296.0f, (float)my_L));
+      uint32_t my_reps = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int32_t s = __shfl_sync(0xFFFFFFFFu, my_s, j);
+        const uint32_t L = __shfl_sync(0xFFFFFFFFu, my_L, j);
+        const uint32_t M = __shfl_sync(0xFFFFFFFFu, my_M, j);
+        const uint32_t valid = __shfl_sync(0xFFFFFFFFu, my_valid, j);
+        const bool sel = valid && s >= c && c < len32;
+        const uint32_t gap = (uint32_t)(s - c);
+        uint32_t qf = __umulhi(gap, M);
+        const int32_t rem = (int32_t)(gap - qf * L);
+        qf += (rem >= (int32_t)L) ? 1u : 0u;
+        qf -= (rem < 0) ? 1u : 0u;
+        const uint32_t kk = qf + 1u;
+        c = sel ? c + (int32_t)(kk * L) : c;
+        const uint32_t reps = sel ? kk : 0u;
+        nsel += sel ? 1u : 0u;
+        nreps += reps;
+        if (lane == j) my_reps = reps;
+      }
+      if (base + lane < cnt) rp[base + lane] = my_reps;
+    }
+  }
+  if (lane == 0) { cb.part_sel[p] = nsel; cb.part_reps[p] = nreps; }
+  return (long long)c + part_pos;
+}
+
 template <int ENGINE>
 __global__ void __launch_bounds__(64) findall_chain4_kernel(const uint64_t n_seg, const uint32_t seg_bytes, const uint32_t G,
                                                             const uint64_t n_parts, const uint32_t mis, const uint64_t len_in,
@@ -273,6 +329,40 @@ __global__ void __launch_bounds__(64) findall_chain4_kernel(const uint64_t n_seg
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t p;
   long long entry;
+  if (ENGINE == FIND_TDFA && pass > 0) {
+    // short worklists: one warp per part (latency mode)
+    const uint32_t cnt = cb.wl_count[pass & 63];
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (cnt <= n_warps && (uint64_t)G * seg_bytes <= (1u << 20)) {
+      const uint64_t wid = t >> 5;
+      if (wid >= cnt) return;
+      p = cb.wl[(size_t)(pass & 1) * n_parts + wid];
+      entry = *reinterpret_cast<volatile long long*>(cb.exitc + (p - 1));
+      const long long used = cb.entry_used[p];
+      __syncwarp();
+      if (entry == used) return;
+      const long long rel = entry - ((long long)(p * G * seg_bytes) - (long long)mis);
+      long long ex;
+      if (rel > -(1ll << 21) && rel < (1ll << 21)) {
+        ex = chain_replay_part_tdfa32_warp(p, entry, n_seg, seg_bytes, G, mis, len_in, fb, cb);
+      } else {
+        ex = 0;
+        if ((threadIdx.x & 31) == 0) ex = chain_replay_part<ENGINE>(p, entry, n_seg, seg_bytes, G, mis, len_in, fb, cb, err);
+        ex = __shfl_sync(0xFFFFFFFFu, ex, 0);
+      }
+      if ((threadIdx.x & 31) == 0) {
+        cb.entry_used[p] = entry;
+        if (cb.exitc[p] != ex) {
+          *reinterpret_cast<volatile long long*>(cb.exitc + p) = ex;
+          if (p + 1 < n_parts) {
+            const uint32_t slot = atomicAdd(&cb.wl_count[(pass + 1) & 63], 1u);
+            cb.wl[(size_t)((pass + 1) & 1) * n_parts + slot] = (uint32_t)(p + 1);
+          }
+        }
+      }
+      return;
+    }
+  }
   if (pass == 0) {
     if (t >= n_parts) return;
     p = t;
