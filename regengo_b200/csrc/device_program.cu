@@ -84,6 +84,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     if (P.char_state[i]) fl |= IF_CHAR_STATE;
     if (in.op == InstAlt) m.n_alt++;
     if (in.op == InstCapture) m.n_capinst++;
+    if (in.op == InstEmptyWidth) m.n_empty++;
     w.push_back((uint32_t)in.op | (fl << 8));
     w.push_back(in.out);
     w.push_back(in.arg);

@@ -48,6 +48,7 @@ struct DevMeta {
   int32_t nullable;            // a match attempt can succeed without consuming input
   int32_t n_alt;               // number of Alt instructions (stack sizing)
   int32_t n_capinst;
+  int32_t n_empty;             // number of EmptyWidth instructions (their outcome depends on the slice origin)
   // "leading class loop + literal" start filter of the backtracking FindAll scan (kernels_btrun.cuh):
   // the program is  (cap|nop)* C+ (cap|nop)* b ...  with b a byte outside the class C
   int32_t run_ok;              // shape recognised

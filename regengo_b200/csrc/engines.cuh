@@ -82,10 +82,14 @@ __device__ __forceinline__ void clear_visited(const Scratch& sc) {
 // int32 relative encoding of offsets kept on the stack and in caps[] (0 for MATCH/FIND, the attempt's
 // searchStart for FINDALL).  caps[] entries are base-relative, CAP_ZERO = Go zero value.
 // Returns 1 on Match.  MODE_FINDALL: one attempt at searchStart (0 => "searchStart++").
-template <int MODE>
+// TRACK (MODE_FINDALL only): *track_fail = offset of the final failure (the generated FindBytesReuse restarts
+// at that offset + 1) and *track_reach = one past the highest input position the attempt looked
+// at (byte reads and end-of-input tests): an attempt whose reach is <= l' behaves identically on in[0:l'].
+template <int MODE, bool TRACK = false>
 __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* __restrict__ in, int64_t l,
                           int64_t search_start, int32_t* caps, const Scratch& sc, int* err, int resume_pc = -1,
-                          int64_t resume_off = 0, uint32_t resume_start_caps = 0) {
+                          int64_t resume_off = 0, uint32_t resume_start_caps = 0, int64_t* track_fail = nullptr,
+                          int64_t* track_reach = nullptr) {
   const int ncap = m.num_cap;
   const bool anchored = (m.flags & F_ANCHORED) != 0;
   const bool needs_bt = (m.flags & F_NEEDS_BT) != 0;
@@ -95,6 +99,7 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
   const int64_t base = MODE == MODE_FINDALL ? search_start : 0;
   const uint4* insts = reinterpret_cast<const uint4*>(img + m.off_inst);
   int64_t offset = 0;
+  int64_t reach = 0;
   uint32_t sp = 0, csp = 0;
   int pc;
 
@@ -129,6 +134,7 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
     switch (op) {
       case OP_MATCH:
         if (MODE != MODE_MATCH) caps[1] = (int32_t)(offset - base);
+        if (TRACK) *track_reach = reach;
         return 1;
       case OP_FAIL:
         if (MODE == MODE_FINDALL) { fail = true; break; }
@@ -149,6 +155,7 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
         break;
       case OP_RUNE1: {
         const uint32_t r = I.w;
+        if (TRACK) reach = max(reach, offset + (r < 128 ? 1 : 4));   // (multi-byte literal: conservative)
         if (r < 128) {
           if (l <= offset || in[offset] != (uint8_t)r) { fail = true; break; }
           offset++;
@@ -166,6 +173,7 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
         break;
       }
       case OP_RUNE: {
+        if (TRACK) reach = max(reach, offset + ((ifl & IF_UNICODE_CLASS) ? 4 : 1));
         if (l <= offset) { fail = true; break; }
         const uint32_t* bm = img + m.off_cls + 8 * pc;
         const uint32_t c = in[offset];
@@ -193,15 +201,18 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
         break;
       }
       case OP_ANY:
+        if (TRACK) reach = max(reach, offset + 1);
         if (l <= offset) { fail = true; break; }
         offset++; pc = (int)I.y;
         break;
       case OP_ANYNOTNL:
+        if (TRACK) reach = max(reach, offset + 1);
         if (l <= offset || in[offset] == '\n') { fail = true; break; }
         offset++; pc = (int)I.y;
         break;
       case OP_EMPTY: {
         const uint32_t a = I.z;
+        if (TRACK) reach = max(reach, offset + 1);
         if ((a & EMPTY_BEGIN_TEXT) && offset != 0) fail = true;
         if ((a & EMPTY_END_TEXT) && offset != l) fail = true;
         if (!fail && (a & EMPTY_BEGIN_LINE) && offset != 0 && in[offset - 1] != '\n') fail = true;
@@ -283,7 +294,10 @@ __device__ int bt_machine(const DevMeta& m, const uint32_t* __restrict__ img, co
       }
       if (resumed) continue;
     }
-    if (MODE == MODE_FINDALL) return 0;
+    if (MODE == MODE_FINDALL) {
+      if (TRACK) { *track_fail = offset; *track_reach = reach; }
+      return 0;
+    }
     if (anchored) return 0;
     if (MODE == MODE_MATCH) {
       if (has_prefix) {

@@ -126,4 +126,167 @@ __global__ void exclusive_scan_u64_kernel(const uint64_t n, const unsigned long 
   if (threadIdx.x == 0) *total = carry;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast FindReader for backtracking patterns (no EmptyWidth, not anchored, not memoised, not nullable).
+//
+// FindBytesReuse on chunk[searchPos:] is a chain of attempts: the attempt at a either matches or fails at
+// an offset f and the next attempt starts at f + 1.  Whether the attempt at a matches, its
+// length and f do not depend on searchPos, and they do not depend on where the chunk ends as long as the
+// attempt never looked at or past that end.  So:
+//   TABLE   one attempt per stream position, all positions in parallel: a 16-bit entry
+//           {match:1 | reach:7 | len-or-next:8} -- reach = how far the attempt looked, len = match length or
+//           next = distance to the next attempt (for a byte that cannot start a match: to the next byte
+//           that can).  Values that do not fit mean "decide inline".
+//   CHASE   one lane per chunk replays the reference loop over the table: follow next-pointers to the first
+//           match (inline exact attempt with the chunk's limit when an entry is marked or reaches the chunk
+//           end), locate the match text with bytes.Index from searchPos (Q16), apply the deferral rule,
+//           move searchPos.  Pass 0 counts, pass 1 lists {searchPos, attempt start, text position}.
+//   RECORDS one lane per listed match re-runs that single attempt on chunk[searchPos:] for the captures.
+// Every step is the reference's own; only the order of evaluation differs.
+constexpr uint32_t RT_SLOW_REACH = 127, RT_SLOW_VAL = 255;
+
+__device__ __forceinline__ Scratch scratch_of(const ScratchPlan& sp) {
+  Scratch sc;
+  sc.stack = sp.stack; sc.cstack = sp.cstack; sc.visited = sp.visited;
+  sc.stack_cap = sp.stack_cap; sc.cstack_cap = sp.cstack_cap; sc.visited_words = sp.visited_words;
+  sc.stride = sp.stride; sc.tid = blockIdx.x * blockDim.x + threadIdx.x;
+  return sc;
+}
+
+// d_stream[0:len) = the shard; entry i describes the attempt at shard position i with the whole shard visible
+__global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
+                                                                const uint8_t* __restrict__ d_stream, const uint64_t len,
+                                                                uint16_t* __restrict__ table, const ScratchPlan sp, int* err) {
+  extern __shared__ __align__(16) uint32_t smem_img[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t* img = gimg;
+  if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
+  const Scratch sc = scratch_of(sp);
+  const uint32_t* first = img + m.off_first;
+  const uint64_t n_units = (len + 63) / 64;     // 64 consecutive positions per thread
+  for (uint64_t u = sc.tid; u < n_units; u += sp.stride) {
+    const uint64_t p0 = u * 64;
+    const uint32_t nb = (uint32_t)min((uint64_t)64, len - p0);
+    // which of my bytes can start a match
+    unsigned long long cand = 0;
+    for (uint32_t j = 0; j < nb; j++) {
+      const uint32_t c = d_stream[p0 + j];
+      if ((first[c >> 5] >> (c & 31)) & 1u) cand |= 1ull << j;
+    }
+    for (uint32_t j = 0; j < nb; j++) {
+      uint32_t entry;
+      if (!((cand >> j) & 1ull)) {
+        const unsigned long long rest = j + 1 < 64 ? cand >> (j + 1) : 0ull;
+        const uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : nb - j;   // next candidate, or my last byte + 1
+        entry = (1u << 8) | dist;                                                  // reach 1, next = dist (<= 64)
+      } else {
+        int32_t caps[MAX_CAPS];
+        int64_t f = 0, reach = 0;
+        const int64_t s = (int64_t)(p0 + j);
+        const int ok = bt_machine<MODE_FINDALL, true>(m, img, d_stream, (int64_t)len, s, caps, sc, err, -1, 0, 0, &f, &reach);
+        const int64_t rr = reach - s;
+        const uint32_t r7 = rr >= (int64_t)RT_SLOW_REACH || rr < 1 ? RT_SLOW_REACH : (uint32_t)rr;
+        if (ok) {
+          const int64_t ml = caps[1];
+          entry = 0x8000u | (r7 << 8) | (ml >= (int64_t)RT_SLOW_VAL || ml < 0 ? RT_SLOW_VAL : (uint32_t)ml);
+        } else {
+          const int64_t nx = f + 1 - s;
+          entry = (r7 << 8) | (nx >= (int64_t)RT_SLOW_VAL || nx < 1 ? RT_SLOW_VAL : (uint32_t)nx);
+        }
+      }
+      table[p0 + j] = (uint16_t)entry;
+    }
+  }
+}
+
+struct ReaderHit { long long search_abs; uint32_t d_true, d_text; unsigned long long chunk; };   // stream offset of searchPos; attempt start / text position relative to it; ChunkIndex
+
+// MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].
+template <int MODE>
+__global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
+                                                                const uint8_t* __restrict__ d_stream, const uint64_t base_off,
+                                                                const uint16_t* __restrict__ table, const ChunkPlan cp,
+                                                                const uint64_t first_chunk, const uint64_t n_run,
+                                                                unsigned long long* __restrict__ counts,
+                                                                const unsigned long long* __restrict__ bases, ReaderHit* __restrict__ hits,
+                                                                const uint64_t cap, const ScratchPlan sp, int* err) {
+  extern __shared__ __align__(16) uint32_t smem_img[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t* img = gimg;
+  if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
+  const Scratch sc = scratch_of(sp);
+  for (uint64_t j = sc.tid; j < n_run; j += sp.stride) {
+    const uint64_t k = first_chunk + j;
+    uint64_t cstart, dlen;
+    bool full;
+    chunk_geometry(cp, k, cstart, dlen, full);
+    const uint8_t* chunk = d_stream + (cstart - base_off);
+    const uint16_t* tab = table + (cstart - base_off);
+    const int64_t data_len = (int64_t)dlen;
+    int64_t pos = 0;
+    unsigned long long n = 0, w = MODE == 1 ? bases[j] : 0;
+    while (pos < data_len) {
+      // FindBytesReuse(chunk[pos:data_len]): attempts at pos, f+1, ...
+      int64_t a = pos, mlen = -1;
+      while (a < data_len) {
+        const uint32_t e = tab[a];
+        const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
+        if (r7 != RT_SLOW_REACH && v != RT_SLOW_VAL && a + (int64_t)r7 <= data_len) {
+          if (e & 0x8000u) { mlen = (int64_t)v; break; }
+          a += (int64_t)v;
+        } else {
+          int32_t caps[MAX_CAPS];
+          int64_t f = 0, reach = 0;
+          if (bt_machine<MODE_FINDALL, true>(m, img, chunk, data_len, a, caps, sc, err, -1, 0, 0, &f, &reach)) { mlen = caps[1]; break; }
+          if (f >= data_len) { a = data_len; break; }   // `if l > offset` fails: FindBytesReuse returns false
+          a = f + 1;
+        }
+      }
+      if (mlen < 0) break;
+      const int64_t mstart = index_of_text(chunk, pos, a, mlen);
+      const int64_t mend = mstart + mlen;
+      if (full && mend > data_len - (int64_t)cp.L) break;  // too close to the boundary: next chunk's job
+      if (MODE == 1 && w < cap) {
+        ReaderHit h;
+        h.search_abs = (long long)cstart + pos; h.d_true = (uint32_t)(a - pos); h.d_text = (uint32_t)(mstart - pos); h.chunk = k;
+        hits[w] = h;
+      }
+      w++; n++;
+      if (mlen > 0) pos = mend; else pos++;
+    }
+    if (MODE == 0) counts[j] = n;
+  }
+}
+
+__global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
+                                                                  const uint8_t* __restrict__ d_stream, const uint64_t base_off,
+                                                                  const ChunkPlan cp, const ReaderHit* __restrict__ hits, const uint64_t n_hits,
+                                                                  int64_t* __restrict__ out_soff, int32_t* __restrict__ out_chunk,
+                                                                  int64_t* __restrict__ out_rec, const ScratchPlan sp, int* err) {
+  extern __shared__ __align__(16) uint32_t smem_img[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t* img = gimg;
+  if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
+  const Scratch sc = scratch_of(sp);
+  const int nc = m.num_cap;
+  for (uint64_t i = sc.tid; i < n_hits; i += sp.stride) {
+    const ReaderHit h = hits[i];
+    const uint64_t k = h.chunk;
+    uint64_t cstart, dlen;
+    bool full;
+    chunk_geometry(cp, k, cstart, dlen, full);
+    (void)full;
+    const int64_t pos = h.search_abs - (long long)cstart;
+    const uint8_t* slice = d_stream + ((uint64_t)h.search_abs - base_off);
+    const int64_t sl = (int64_t)dlen - pos;
+    int32_t caps[MAX_CAPS];
+    int64_t rec[MAX_CAPS];
+    bt_machine<MODE_FINDALL>(m, img, slice, sl, (int64_t)h.d_true, caps, sc, err);
+    bt_emit_record(caps, nc, (int64_t)h.d_true, sl, 0, rec);
+    out_soff[i] = h.search_abs + (long long)h.d_text;
+    out_chunk[i] = (int32_t)k;
+    for (int g = 0; g < nc; g++) out_rec[i * nc + g] = rec[g] < 0 ? -1 : h.search_abs + rec[g];
+  }
+}
+
 }  // namespace rgx
