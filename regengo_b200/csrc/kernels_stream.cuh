@@ -201,7 +201,23 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
 
 struct ReaderHit { long long search_abs; uint32_t d_true, d_text; unsigned long long chunk; };   // stream offset of searchPos; attempt start / text position relative to it; ChunkIndex
 
+// bytes.Index(hay[from:], hay[ns:ns+nl]) by a whole warp: lane i tests from + i, from + 32 + i, ...
+__device__ __forceinline__ int64_t warp_index_of_text(const uint8_t* hay, int64_t from, int64_t ns, int64_t nl, int lane) {
+  if (nl == 0) return from;
+  for (int64_t b = from; b < ns; b += 32) {
+    const int64_t q = b + lane;
+    bool eq = q < ns;
+    for (int64_t j = 0; eq && j < nl; j++) eq = hay[q + j] == hay[ns + j];
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, eq);
+    if (bal) return b + (__ffs(bal) - 1);
+  }
+  return ns;
+}
+
 // MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].
+// One WARP per chunk.  The replay is sequential, but its memory accesses are not: the lanes fetch 32 table
+// entries at a time (one coalesced load) and the attempt chain is followed through them with shuffles; the
+// bytes.Index scan tests 32 positions per step.  All control flow is warp-uniform.
 template <int MODE>
 __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                 const uint8_t* __restrict__ d_stream, const uint64_t base_off,
@@ -215,7 +231,8 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
   const uint32_t* img = gimg;
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
-  for (uint64_t j = sc.tid; j < n_run; j += sp.stride) {
+  const int lane = threadIdx.x & 31;
+  for (uint64_t j = sc.tid >> 5; j < n_run; j += sp.stride >> 5) {
     const uint64_t k = first_chunk + j;
     uint64_t cstart, dlen;
     bool full;
@@ -225,11 +242,18 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
     const int64_t data_len = (int64_t)dlen;
     int64_t pos = 0;
     unsigned long long n = 0, w = MODE == 1 ? bases[j] : 0;
-    while (pos < data_len) {
+    bool stop = false;
+    while (!stop && pos < data_len) {
       // FindBytesReuse(chunk[pos:data_len]): attempts at pos, f+1, ...
       int64_t a = pos, mlen = -1;
+      int64_t wb = -64;
+      uint32_t ew = 0;
       while (a < data_len) {
-        const uint32_t e = tab[a];
+        if (a >= wb + 32) {   // fetch the 32 entries from a on
+          wb = a;
+          ew = wb + lane < data_len ? tab[wb + lane] : 0u;
+        }
+        const uint32_t e = __shfl_sync(0xFFFFFFFFu, ew, (int)(a - wb));
         const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
         if (r7 != RT_SLOW_REACH && v != RT_SLOW_VAL && a + (int64_t)r7 <= data_len) {
           if (e & 0x8000u) { mlen = (int64_t)v; break; }
@@ -243,10 +267,10 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
         }
       }
       if (mlen < 0) break;
-      const int64_t mstart = index_of_text(chunk, pos, a, mlen);
+      const int64_t mstart = warp_index_of_text(chunk, pos, a, mlen, lane);
       const int64_t mend = mstart + mlen;
       if (full && mend > data_len - (int64_t)cp.L) break;  // too close to the boundary: next chunk's job
-      if (MODE == 1 && w < cap) {
+      if (MODE == 1 && w < cap && lane == 0) {
         ReaderHit h;
         h.search_abs = (long long)cstart + pos; h.d_true = (uint32_t)(a - pos); h.d_text = (uint32_t)(mstart - pos); h.chunk = k;
         hits[w] = h;
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
       w++; n++;
       if (mlen > 0) pos = mend; else pos++;
     }
-    if (MODE == 0) counts[j] = n;
+    if (MODE == 0 && lane == 0) counts[j] = n;
   }
 }
 
