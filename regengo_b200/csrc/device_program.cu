@@ -312,6 +312,62 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
         if (ok) { m.run_ok = 1; m.run_class_pc = L; m.run_lit = (int32_t)b; m.run_start_caps = start_caps; m.run_resume_pc = (int)prog.inst[A].arg; }
       }
     }
+    // Straight-line continuation after the leading loop?  Elements: Capture, ASCII literal byte, ASCII class,
+    // and "C+" = class instruction L followed by Alt(out = L, arg = exit) with L looping straight back to the
+    // Alt, where the loop is ATOMIC: the exit leads through captures/nops either to a literal byte outside C
+    // or to Match.  Then a shorter run of the loop can never help (it would resume on a byte of C where a byte
+    // outside C is required; before Match the greedy choice succeeds outright), so the goto-machine's first
+    // successful path is the greedy one and every other path fails: direct evaluation gives the same verdict,
+    // the same end and the same captures (instructions.go:331-457, find.go:351-466).
+    if (m.run_ok) {
+      std::vector<uint32_t> lin;
+      int pc = m.run_resume_pc;
+      bool ok = true, done = false;
+      std::vector<uint8_t> seen(n, 0);
+      while (ok && !done && lin.size() < 39) {
+        if (seen[pc]) { ok = false; break; }
+        seen[pc] = 1;
+        const Inst& in = prog.inst[pc];
+        switch (in.op) {
+          case InstNop: pc = (int)in.out; break;
+          case InstCapture: if (in.arg >= 32) ok = false; lin.push_back(LIN_CAP | (in.arg << 8)); pc = (int)in.out; break;
+          case InstRune1:
+            if (in.rune.size() != 1 || in.rune[0] >= 128) { ok = false; break; }
+            lin.push_back(LIN_LIT | ((uint32_t)in.rune[0] << 8)); pc = (int)in.out; break;
+          case InstRune: {
+            if (P.unicode_class[pc]) { ok = false; break; }
+            lin.push_back(LIN_CLS | ((uint32_t)pc << 8));
+            const int A2 = (int)in.out;
+            const Inst& a2 = prog.inst[A2];
+            if (a2.op == InstAlt && (int)a2.out == pc && indeg[A2] == 1 && indeg[pc] == 2) {
+              // C+ : is the loop atomic?
+              int q = (int)a2.arg;
+              size_t g2 = 0;
+              while (g2++ <= n && (prog.inst[q].op == InstCapture || prog.inst[q].op == InstNop)) q = (int)prog.inst[q].out;
+              const Inst& nx = prog.inst[q];
+              bool atomic = nx.op == InstMatch;
+              if (nx.op == InstRune1 && nx.rune.size() == 1 && nx.rune[0] < 128) {
+                const uint32_t b2 = (uint32_t)nx.rune[0];
+                atomic = !((P.class_bits[(size_t)pc * 8 + (b2 >> 5)] >> (b2 & 31)) & 1u);
+              }
+              if (!atomic) { ok = false; break; }
+              lin.push_back(LIN_LOOP | ((uint32_t)pc << 8));
+              seen[A2] = 1;
+              pc = (int)a2.arg;
+            } else {
+              pc = A2;
+            }
+            break;
+          }
+          case InstMatch: lin.push_back(LIN_MATCH); done = true; break;
+          default: ok = false; break;
+        }
+      }
+      if (ok && done) {
+        m.lin_n = (int32_t)lin.size();
+        for (size_t i = 0; i < lin.size(); i++) m.lin[i] = lin[i];
+      }
+    }
   }
 }
 

@@ -25,6 +25,7 @@ constexpr uint32_t FAST_NONE = 0x3FFu;   // next-state field of a fast cell with
 constexpr uint32_t SMEM_IMAGE_LIMIT = 160 * 1024;
 
 enum GenKind : int { GEN_ALL = 0, GEN_BYTESET = 1, GEN_PREFIX = 2 };
+enum LinKind : uint32_t { LIN_CAP = 0, LIN_LIT = 1, LIN_CLS = 2, LIN_LOOP = 3, LIN_MATCH = 4 };
 
 struct DevMeta {
   int32_t n_inst, start, num_cap, flags, prefix, match_engine, find_engine;
@@ -56,6 +57,11 @@ struct DevMeta {
   int32_t run_lit;             // b
   uint32_t run_start_caps;     // capture slots written before the loop (they hold the attempt's start)
   int32_t run_resume_pc;       // instruction after the loop (the Alt's exit): attempts of a run resume here at offset p
+  // When everything after the leading loop is a straight line of captures, literal bytes, ASCII classes and
+  // ATOMIC greedy class loops (device_program.cu), the attempt has exactly one path that can succeed -- the
+  // greedy one -- and is evaluated directly instead of by the goto-machine: lin[i] = kind | arg << 8.
+  int32_t lin_n;               // 0: not linear
+  uint32_t lin[40];
 };
 
 struct DeviceImage {

@@ -149,7 +149,47 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
         int32_t caps[MAX_CAPS];
         const uint64_t r = seg * fb.K + k;
         uint2 key = make_uint2(0, KEY_INVALID);
-        if (bt_machine<MODE_FINDALL>(m, img, buf, (int64_t)len, s0, caps, sc, err, m.run_resume_pc, p, m.run_start_caps)) {
+        bool matched;
+        if (m.lin_n > 0) {
+          // straight-line continuation (device_program.cu): the greedy path is the only one that can succeed
+          for (int i = 0; i < nc; i++) caps[i] = ((m.run_start_caps >> i) & 1u) ? 0 : CAP_ZERO;
+          int64_t pos = p;
+          matched = false;
+          bool alive = true;
+          for (int e = 0; e < m.lin_n && alive; e++) {
+            const uint32_t el = m.lin[e], arg = el >> 8;
+            switch (el & 255u) {
+              case LIN_CAP: caps[arg] = (int32_t)(pos - s0); break;
+              case LIN_LIT:
+                if (pos >= (int64_t)len || buf[pos] != (uint8_t)arg) alive = false; else pos++;
+                break;
+              case LIN_CLS: {
+                const uint32_t* bm = img + m.off_cls + 8 * arg;
+                const uint32_t c = pos < (int64_t)len ? buf[pos] : 256u;
+                if (c > 255u || !((bm[c >> 5] >> (c & 31)) & 1u)) alive = false; else pos++;
+                break;
+              }
+              case LIN_LOOP: {
+                const uint32_t* bm = img + m.off_cls + 8 * arg;
+                while (pos < (int64_t)len) {
+                  const uint32_t c = buf[pos];
+                  if (!((bm[c >> 5] >> (c & 31)) & 1u)) break;
+                  pos++;
+                }
+                break;
+              }
+              default:   // LIN_MATCH
+                caps[1] = (int32_t)(pos - s0);
+                matched = true;
+                alive = false;
+                break;
+            }
+          }
+          if (pos - s0 > 0x7FFFFFFFll) { atomicOr(err, ERR_RANGE); matched = false; }
+        } else {
+          matched = bt_machine<MODE_FINDALL>(m, img, buf, (int64_t)len, s0, caps, sc, err, m.run_resume_pc, p, m.run_start_caps) != 0;
+        }
+        if (matched) {
           const int64_t first_rel = s0 - ((int64_t)seg_a - (int64_t)mis);   // may be negative: the run began in an earlier segment
           const int64_t run_extra = p - 1 - s0;
           const int64_t mlen = caps[1];
