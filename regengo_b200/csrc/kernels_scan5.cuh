@@ -114,29 +114,40 @@ __global__ void __launch_bounds__(SCAN5_WARPS * 32, 4) findall_scan5_kernel(
         const bool do_b = active && (exit_step || selfcell == NOSELF);
         if (!__any_sync(0xFFFFFFFFu, do_b)) {
           if (!__any_sync(0xFFFFFFFFu, active)) break;
-          // phase A: boring bytes, four per iteration; the cell that ends the run is handed to phase B
+          // phase A: boring bytes, eight per iteration (eight independent cell loads in flight); the cell that
+          // ends the run is handed to phase B
           if (active) {
             uint32_t a = ri & ~3u;
-            if (a + 16 <= lim) {
+            if (a + 24 <= lim) {
               const uint32_t sh = (ri & 3u) * 8u;
-              uint32_t lo = *reinterpret_cast<const uint32_t*>(segp + a);
-              uint32_t hi = *reinterpret_cast<const uint32_t*>(segp + a + 4);
-              uint32_t hi2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
+              uint32_t x0 = *reinterpret_cast<const uint32_t*>(segp + a);
+              uint32_t x1 = *reinterpret_cast<const uint32_t*>(segp + a + 4);
+              uint32_t x2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
+              uint32_t x3 = *reinterpret_cast<const uint32_t*>(segp + a + 12);
               for (;;) {
-                const uint32_t w = __funnelshift_r(lo, hi, sh);
-                if (w & 0x80808080u) break;
-                const uint32_t c0 = lds_u32(row + ((w << 2) & 0x3FCu));
-                const uint32_t c1 = lds_u32(row + ((w >> 6) & 0x3FCu));
-                const uint32_t c2 = lds_u32(row + ((w >> 14) & 0x3FCu));
-                const uint32_t c3 = lds_u32(row + ((w >> 22) & 0x3FCu));
+                const uint32_t w0 = __funnelshift_r(x0, x1, sh), w1 = __funnelshift_r(x1, x2, sh);
+                if ((w0 | w1) & 0x80808080u) break;
+                const uint32_t c0 = lds_u32(row + ((w0 << 2) & 0x3FCu));
+                const uint32_t c1 = lds_u32(row + ((w0 >> 6) & 0x3FCu));
+                const uint32_t c2 = lds_u32(row + ((w0 >> 14) & 0x3FCu));
+                const uint32_t c3 = lds_u32(row + ((w0 >> 22) & 0x3FCu));
+                const uint32_t c4 = lds_u32(row + ((w1 << 2) & 0x3FCu));
+                const uint32_t c5 = lds_u32(row + ((w1 >> 6) & 0x3FCu));
+                const uint32_t c6 = lds_u32(row + ((w1 >> 14) & 0x3FCu));
+                const uint32_t c7 = lds_u32(row + ((w1 >> 22) & 0x3FCu));
                 if (c0 != selfcell) { pre_cell = c0; break; }
                 if (c1 != selfcell) { pre_cell = c1; ri += 1; break; }
                 if (c2 != selfcell) { pre_cell = c2; ri += 2; break; }
                 if (c3 != selfcell) { pre_cell = c3; ri += 3; break; }
-                ri += 4; a += 4;
-                if (a + 16 > lim) break;
-                lo = hi; hi = hi2;
-                hi2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
+                if (c4 != selfcell) { pre_cell = c4; ri += 4; break; }
+                if (c5 != selfcell) { pre_cell = c5; ri += 5; break; }
+                if (c6 != selfcell) { pre_cell = c6; ri += 6; break; }
+                if (c7 != selfcell) { pre_cell = c7; ri += 7; break; }
+                ri += 8; a += 8;
+                if (a + 24 > lim) break;
+                x0 = x2; x1 = x3;
+                x2 = *reinterpret_cast<const uint32_t*>(segp + a + 8);
+                x3 = *reinterpret_cast<const uint32_t*>(segp + a + 12);
               }
             }
           }
