@@ -27,7 +27,7 @@ constexpr uint32_t SEGB_BYTES = 32768;   // ~80 candidates per segment on log te
 constexpr uint32_t QBCAP = 1024;
 constexpr int BTRUN_WARPS = 8;
 
-__global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
+__global__ void __launch_bounds__(BTRUN_WARPS * 32, 4) findall_scan_btrun_kernel(
     const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem, const uint8_t* __restrict__ buf, const uint64_t len,
     const uint32_t mis, const uint64_t n_seg, const FindAllBufs fb, const ScratchPlan sp, int* err) {
   extern __shared__ __align__(16) uint32_t smem_all[];
@@ -47,9 +47,6 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
   const uint32_t pb = (uint32_t)m.run_lit * 0x01010101u;
   const uint32_t* cls = img + m.off_cls + 8 * m.run_class_pc;
   const uint64_t total_warps = (uint64_t)gridDim.x * BTRUN_WARPS;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  constexpr uint32_t N_IT = SEGB_BYTES / 512;
-  constexpr int U = 4;
   const int nc = m.num_cap;
 
   for (uint64_t seg = (uint64_t)blockIdx.x * BTRUN_WARPS + warp; seg < n_seg; seg += total_warps) {
@@ -57,9 +54,13 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
     const bool interior = seg_a >= mis && seg_a + SEGB_BYTES <= end_a;
     uint32_t tail = 0;
     bool dense = false;
-    auto load16 = [&](uint32_t it) -> uint4 {
-      const uint64_t apos = seg_a + (uint64_t)it * 512 + (uint64_t)lane * 16;
-      if (interior || (apos >= mis && apos + 16 <= end_a)) return *reinterpret_cast<const uint4*>(abuf + apos);
+    // FILTER: positions p with input[p] == b.  A lane owns 64 contiguous bytes of each 2 KiB block; SWAR
+    // zero-byte test on w ^ b (the cheap test can only err on the byte right above a true hit, i.e. when two
+    // hits touch; that redoes the block with the exact test), flags packed to two words per lane (bit
+    // 8*byte + word), ordered append through a warp prefix sum.  Whether a class run ends at p is left to
+    // the verify step (an empty run is no candidate).
+    const bool interior_ld = interior;
+    auto load_guarded = [&](const uint64_t apos) -> uint4 {
       uint4 v = make_uint4(0, 0, 0, 0);
       if (apos + 16 > mis && apos < end_a) {
         uint8_t* vb = reinterpret_cast<uint8_t*>(&v);
@@ -67,72 +68,77 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
       }
       return v;
     };
-    // FILTER: positions p with input[p] == b (approximate compare; verified below)
-    uint4 nxt[U];
+    uint32_t w[16];
+    auto load_block = [&](const uint32_t blk) {
+      const uint64_t off = seg_a + (uint64_t)blk * 2048 + (uint64_t)lane * 64;
 #pragma unroll
-    for (int u = 0; u < U; u++) nxt[u] = load16(u);
-    for (uint32_t it0 = 0; it0 < N_IT; it0 += U) {
-      uint4 cur[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) cur[u] = nxt[u];
-      if (it0 + U < N_IT) {
-#pragma unroll
-        for (int u = 0; u < U; u++) nxt[u] = load16(it0 + U + u);
+      for (int u = 0; u < 4; u++) {
+        const uint64_t apos = off + u * 16;
+        const uint4 v = (interior_ld || (apos >= mis && apos + 16 <= end_a)) ? *reinterpret_cast<const uint4*>(abuf + apos) : load_guarded(apos);
+        w[4 * u] = v.x; w[4 * u + 1] = v.y; w[4 * u + 2] = v.z; w[4 * u + 3] = v.w;
       }
-      uint32_t cc[U][4];
-      uint32_t any_all = 0;
+    };
+    constexpr uint32_t N_BLK = SEGB_BYTES / 2048;
+    const bool zero_lit = m.run_lit == 0;   // out-of-range bytes read as 0: clip even interior-looking hits then
+    load_block(0);
+    for (uint32_t blk = 0; blk < N_BLK; blk++) {
+      uint32_t e0 = 0, e1 = 0;
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        cc[u][0] = eq_approx(cur[u].x, pb); cc[u][1] = eq_approx(cur[u].y, pb);
-        cc[u][2] = eq_approx(cur[u].z, pb); cc[u][3] = eq_approx(cur[u].w, pb);
-        any_all |= cc[u][0] | cc[u][1] | cc[u][2] | cc[u][3];
+      for (int j = 0; j < 16; j++) {
+        const uint32_t z = w[j] ^ pb;
+        const uint32_t d = (z - 0x01010101u) & ~z & 0x80808080u;
+        if (j < 8) e0 |= d >> (7 - j); else e1 |= d >> (15 - j);
       }
-      if (__ballot_sync(0xFFFFFFFFu, any_all != 0)) {
+      if ((e0 & (e0 >> 8)) | (e1 & (e1 >> 8))) {
+        e0 = 0; e1 = 0;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          uint32_t mask = 0;
-          if (cc[u][0] | cc[u][1] | cc[u][2] | cc[u][3]) {
-            mask = gather4(cc[u][0]) | (gather4(cc[u][1]) << 4) | (gather4(cc[u][2]) << 8) | (gather4(cc[u][3]) << 12);
-            const uint64_t apos = seg_a + (uint64_t)(it0 + u) * 512 + (uint64_t)lane * 16;
-            // exact test of b, and the byte before it must belong to C (else no run ends here)
-            uint32_t mm = mask;
-            while (mm) {
-              const int j = __ffs(mm) - 1;
-              mm &= mm - 1;
-              const uint64_t ap = apos + j;
-              bool ok = ap > mis && ap < end_a && abuf[ap] == (uint8_t)m.run_lit;
-              if (ok) { const uint32_t pc = abuf[ap - 1]; ok = (cls[pc >> 5] >> (pc & 31)) & 1u; }
-              if (!ok) mask &= ~(1u << j);
-            }
+        for (int j = 0; j < 16; j++) {
+          const uint32_t z = w[j] ^ pb;
+          const uint32_t d = ~(((z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | z | 0x7F7F7F7Fu);
+          if (j < 8) e0 |= d >> (7 - j); else e1 |= d >> (15 - j);
+        }
+      }
+      if (blk + 1 < N_BLK) load_block(blk + 1);
+      if ((!interior || zero_lit) && (e0 | e1)) {
+        const uint64_t apos = seg_a + (uint64_t)blk * 2048 + (uint64_t)lane * 64;
+        for (int half = 0; half < 2; half++) {
+          uint32_t e = half ? e1 : e0, keep = 0;
+          while (e) {
+            const uint32_t b = __ffs(e) - 1;
+            e &= e - 1;
+            const uint64_t ap = apos + half * 32 + 4 * (b & 7u) + (b >> 3);
+            if (ap >= mis && ap < end_a) keep |= 1u << b;
           }
-          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mask != 0);
-          if (bal) {
-            const uint32_t multi = __ballot_sync(0xFFFFFFFFu, (mask & (mask - 1)) != 0);
-            if (!multi) {
-              const uint32_t slot = tail + __popc(bal & lt_mask);
-              if (mask && slot < QBCAP) q[slot] = (uint16_t)((it0 + u) * 512 + lane * 16 + __ffs(mask) - 1);
-              tail += __popc(bal);
-            } else {
-              const uint32_t c = __popc(mask);
-              uint32_t incl = c;
+          if (half) e1 = keep; else e0 = keep;
+        }
+      }
+      const uint32_t c = __popc(e0) + __popc(e1);
+      if (__ballot_sync(0xFFFFFFFFu, c != 0)) {
+        uint32_t incl = c;
 #pragma unroll
-              for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
-              uint32_t w = tail + incl - c;
-              while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (w < QBCAP) q[w] = (uint16_t)((it0 + u) * 512 + lane * 16 + j);
-                w++;
-              }
-              tail += __shfl_sync(0xFFFFFFFFu, incl, 31);
-            }
-            if (tail > QBCAP) dense = true;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (c) {
+          const uint32_t wb = tail + incl - c;
+          uint32_t pbase = blk * 2048 + lane * 64;
+          uint32_t i = 0, e = e0;
+          for (;;) {
+            if (!e) { if (!e1) break; e = e1; e1 = 0; pbase += 32; }
+            const uint32_t b = __ffs(e) - 1;
+            e &= e - 1;
+            const uint32_t pos = pbase + 4 * (b & 7u) + (b >> 3);
+            uint32_t j = i;
+            while (j > 0 && wb + j - 1 < QBCAP && q[wb + j - 1] > pos) { if (wb + j < QBCAP) q[wb + j] = q[wb + j - 1]; j--; }
+            if (wb + j < QBCAP) q[wb + j] = (uint16_t)pos;
+            i++;
           }
         }
+        tail += total;
+        if (tail > QBCAP) { dense = true; tail = QBCAP; }
       }
     }
     __syncwarp();
-    if (dense) { if (lane == 0) atomicOr(err, ERR_DENSE); tail = QBCAP; }
+    if (dense && lane == 0) atomicOr(err, ERR_DENSE);
 
     // VERIFY: walk back to the start of the C-run, one exact attempt of the goto-machine from there
     const uint32_t n = tail;
@@ -150,7 +156,9 @@ __global__ void __launch_bounds__(BTRUN_WARPS * 32) findall_scan_btrun_kernel(
         const uint64_t r = seg * fb.K + k;
         uint2 key = make_uint2(0, KEY_INVALID);
         bool matched;
-        if (m.lin_n > 0) {
+        if (s0 == p) {
+          matched = false;   // no class byte before b: C+ cannot match here
+        } else if (m.lin_n > 0) {
           // straight-line continuation (device_program.cu): the greedy path is the only one that can succeed
           for (int i = 0; i < nc; i++) caps[i] = ((m.run_start_caps >> i) & 1u) ? 0 : CAP_ZERO;
           int64_t pos = p;

@@ -195,145 +195,6 @@ struct ChainBufs {
   int* changed;
 };
 
-// One thread per part of G consecutive segments.
-template <int ENGINE>
-__global__ void findall_chain_kernel(const uint64_t n_seg, const uint32_t G, const uint64_t n_parts, const uint32_t mis,
-                                     const uint64_t len, const FindAllBufs fb, const ChainBufs cb, const int pass, int* err) {
-  const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_parts) return;
-  const uint64_t seg0 = p * G, seg1 = min(seg0 + G, n_seg);
-  // entry cursor (buffer-relative): part 0 starts at 0; later parts speculate "the predecessor ended
-  // exactly at my first byte" in pass 0 and take the predecessor's last exit afterwards
-  long long cursor;
-  if (p == 0) cursor = 0;
-  else if (pass == 0) cursor = (long long)(seg0 * SEG_BYTES) - (long long)mis;
-  else cursor = cb.exit_prev[p - 1];
-  if (cursor < 0) cursor = 0;
-  unsigned long long nsel = 0, nreps = 0;
-  for (uint64_t seg = seg0; seg < seg1; seg++) {
-    const uint32_t c = fb.count[seg];
-    const long long seg_pos = (long long)(seg * SEG_BYTES) - (long long)mis;
-    for (uint32_t r = 0; r < c; r++) {
-      const uint2 k = fb.keys[seg * fb.K + r];
-      const long long s = seg_pos + (long long)k.x;
-      uint32_t reps = 0;
-      if (s >= cursor && (unsigned long long)cursor < len) {
-        if (ENGINE == FIND_TDFA) {
-          // offset += len(match) from the SLICE start (compiler.go:630-636): the record at s is
-          // returned once per cursor value o, o+L, ... <= s
-          const unsigned long long L = k.y ? k.y : 1;
-          const unsigned long long kk = (unsigned long long)(s - cursor) / L + 1;
-          if (kk > 0xFFFFFFFFull) { atomicOr(err, ERR_RANGE); }
-          reps = (uint32_t)kk;
-          cursor += (long long)(kk * L);
-        } else {
-          // searchStart = captures[1] if it advanced, else searchStart+1 (find.go:452-457)
-          reps = 1;
-          cursor = k.y ? s + (long long)k.y : s + 1;
-        }
-        nsel++;
-        nreps += reps;
-      }
-      fb.reps[seg * fb.K + r] = reps;
-    }
-  }
-  cb.exit_cur[p] = cursor;
-  if (pass > 0 && cb.exit_prev[p] != cursor) atomicOr(cb.changed, 1);
-  cb.part_sel[p] = nsel;
-  cb.part_reps[p] = nreps;
-}
-
-// exclusive scan of the per-part counts (single CTA; n_parts is len / (G*SEG), i.e. thousands)
-__global__ void findall_part_scan_kernel(const uint64_t n_parts, const unsigned long long* __restrict__ part_sel,
-                                         const unsigned long long* __restrict__ part_reps, unsigned long long* sel_base,
-                                         unsigned long long* reps_base, unsigned long long* totals) {
-  __shared__ unsigned long long s_sel[1024], s_reps[1024];
-  __shared__ unsigned long long carry_sel, carry_reps;
-  if (threadIdx.x == 0) { carry_sel = 0; carry_reps = 0; }
-  __syncthreads();
-  for (uint64_t base = 0; base < n_parts; base += 1024) {
-    const uint64_t i = base + threadIdx.x;
-    const unsigned long long a = i < n_parts ? part_sel[i] : 0, b = i < n_parts ? part_reps[i] : 0;
-    s_sel[threadIdx.x] = a; s_reps[threadIdx.x] = b;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      unsigned long long x = 0, y = 0;
-      if ((int)threadIdx.x >= o) { x = s_sel[threadIdx.x - o]; y = s_reps[threadIdx.x - o]; }
-      __syncthreads();
-      s_sel[threadIdx.x] += x; s_reps[threadIdx.x] += y;
-      __syncthreads();
-    }
-    if (i < n_parts) { sel_base[i] = carry_sel + s_sel[threadIdx.x] - a; reps_base[i] = carry_reps + s_reps[threadIdx.x] - b; }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_sel += s_sel[1023]; carry_reps += s_reps[1023]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { totals[0] = carry_sel; totals[1] = carry_reps; }
-}
-
-// ---- phase 3: ordered compaction into int64 offset records --------------------------------------------
-// One warp per part.  n_limit < 0: everything; otherwise the expanded list is cut after n_limit
-// matches (a record's reps are clipped, later records dropped).
-template <int ENGINE>
-__global__ void findall_emit_kernel(const DevMeta m, const uint64_t n_seg, const uint32_t G, const uint64_t n_parts,
-                                    const uint32_t mis, const uint64_t len, const FindAllBufs fb,
-                                    const unsigned long long* __restrict__ sel_base, const unsigned long long* __restrict__ reps_base,
-                                    const long long n_limit, int64_t* __restrict__ out, uint32_t* __restrict__ out_reps,
-                                    const uint64_t cap_records, unsigned long long* n_written) {
-  const uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (p >= n_parts) return;
-  const uint64_t seg0 = p * G, seg1 = min(seg0 + G, n_seg);
-  unsigned long long o = sel_base[p];    // index of the next kept record
-  unsigned long long cum = reps_base[p]; // matches returned before it
-  const int nc = ENGINE == FIND_TDFA ? m.t_ntags : m.num_cap;
-  for (uint64_t seg = seg0; seg < seg1; seg++) {
-    const uint32_t c = fb.count[seg];
-    const long long seg_pos = (long long)(seg * SEG_BYTES) - (long long)mis;
-    for (uint32_t r0 = 0; r0 < c; r0 += 32) {
-      const uint32_t r = r0 + lane;
-      uint32_t reps = r < c ? fb.reps[seg * fb.K + r] : 0;
-      // exclusive prefix of kept flags and of reps inside this group of 32
-      const uint32_t bal = __ballot_sync(0xFFFFFFFFu, reps != 0);
-      const uint32_t before = __popc(bal & ((1u << lane) - 1u));
-      unsigned long long incl = reps;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += y; }
-      const unsigned long long my_cum = cum + incl - reps;
-      if (reps != 0) {
-        bool keep = true;
-        if (n_limit >= 0) {
-          if (my_cum >= (unsigned long long)n_limit) keep = false;
-          else if (my_cum + reps > (unsigned long long)n_limit) reps = (uint32_t)((unsigned long long)n_limit - my_cum);
-        }
-        const unsigned long long idx = o + before;
-        if (keep) {
-          atomicMax(n_written, idx + 1);
-          if (idx < cap_records) {
-            const uint64_t rr = seg * fb.K + r;
-            const uint2 k = fb.keys[rr];
-            const long long s = seg_pos + (long long)k.x, e = s + (long long)k.y;
-            int64_t* dst = out + idx * (uint64_t)nc;
-            dst[0] = s; dst[1] = e;
-            for (int g = 1; g < nc / 2; g++) {
-              const int32_t a = fb.caps[rr * fb.cw + 2 * g - 2], b = fb.caps[rr * fb.cw + 2 * g - 1];
-              if (ENGINE == FIND_TDFA) {
-                if (a >= 0) { dst[2 * g] = s + a; dst[2 * g + 1] = s + b; } else { dst[2 * g] = -1; dst[2 * g + 1] = -1; }
-              } else {
-                const long long av = a == CAP_ZERO ? 0 : s + a, bv = b == CAP_ZERO ? 0 : s + b;
-                if (av <= bv && bv <= (long long)len) { dst[2 * g] = av; dst[2 * g + 1] = bv; } else { dst[2 * g] = -1; dst[2 * g + 1] = -1; }
-              }
-            }
-            out_reps[idx] = reps;
-          }
-        }
-      }
-      o += __popc(bal);
-      cum += __shfl_sync(0xFFFFFFFFu, incl, 31);
-    }
-  }
-}
-
 // ---- generic exact fallback: the reference loop, literally, on ONE device thread ---------------------
 // Used for patterns the parallel path does not cover (anchored, memoised FindAll whose visited bits
 // persist across iterations -- SURVEY Q12, TDFA whose begin/any start states differ -- Q3).

@@ -1,7 +1,7 @@
 // findall_scan5_kernel -- the FindAll scan for TDFA patterns with a >= 2-byte literal start filter
-// (fifth iteration; same contract and record format as findall_scan4_kernel).
+// (one warp per 32 KiB segment; slab entry j of a segment = candidate j: {start_rel, len}, capture offsets).
 //
-// scan4 was issue-bound (0.83 warp instructions per input byte, profiles/r1_b_ncu_scan4_c3.txt); this
+// Its predecessor was issue-bound (0.83 warp instructions per input byte, profiles/r1_b_ncu_scan4_c3.txt); this
 // version cuts the instruction count of both halves:
 //
 //   FILTER  a lane owns 64 contiguous bytes of every 2 KiB block (four 16-byte loads plus the word that
@@ -26,11 +26,13 @@
 // (position ri when the run ends) is observable; phase B sets acc_ri = ri before it looks at the byte
 // that ends the run.
 #pragma once
-#include "kernels_scan4.cuh"
+#include "kernels_findall2.cuh"
 
 namespace rgx {
 
 constexpr int SCAN5_WARPS = 8;
+constexpr uint32_t Q4CAP = 1024;      // candidates per segment before the host falls back to the generic scan
+constexpr int LOG4CAP = 12;           // tag events per walk
 constexpr uint32_t BLK5 = 2048;          // bytes per filter block (64 per lane)
 constexpr uint32_t NOSELF = 0xFFFFFFFFu;
 constexpr uint32_t NOCELL = 0xFFFFFFFEu;   // no cell value has transition list 0x3FF and next state 0x3FE
