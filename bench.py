@@ -242,7 +242,8 @@ def main():
             L.rgx_ctx_last_timing(ctx, phase)
             step_phase[2] = phase[2]
             return r
-        _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64, finish=finish)
+        _, _, total_local, rounds = rdist.resolve_cursor_chain(resolve, rank, world, shard_start, gather_i64, finish=finish,
+                                                                   all_starts=[r * n_bytes for r in range(world)])
         exchange_rounds[0] = rounds
         return total_local
 

@@ -76,7 +76,7 @@ def chunk_span(first, count, buffer_size, max_leftover, total_len):
     return min(lo, total_len), hi
 
 
-def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, first_guess=None, finish=None):
+def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, first_guess=None, finish=None, all_starts=None):
     """Make every rank's entry cursor equal its predecessor's exit cursor.
 
     resolve(entry_global) -> (exit_global, payload): replays this rank's records from `entry_global`
@@ -84,8 +84,13 @@ def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, firs
     finish() -> payload (optional): when given, `resolve` only replays the cursor and `finish` produces
     the output once, after the entries have settled (saves the output pass of every discarded round).
     all_gather_i64(v) -> list of every rank's v (a collective; every rank calls it the same number of
-    times).  Returns (entry, exit, payload, rounds)."""
+    times).  all_starts (optional): every rank's shard_start; with it each rank can tell from the gathered
+    exits alone whether ANY rank still has to redo its replay, so a round costs one collective instead of two.
+    Returns (entry, exit, payload, rounds)."""
     entry = 0 if rank == 0 else (shard_start if first_guess is None else first_guess)
+    entries = None
+    if all_starts is not None and first_guess is None:
+        entries = [0] + [int(x) for x in all_starts[1:]]
     rounds = 0
     exit_cur, payload = resolve(entry)
     while True:
@@ -93,7 +98,12 @@ def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, firs
         exits = all_gather_i64(exit_cur)
         want = 0 if rank == 0 else int(exits[rank - 1])
         changed = int(want != entry)
-        any_changed = max(all_gather_i64(changed))
+        if entries is not None:
+            wants = [0] + [int(exits[r - 1]) for r in range(1, world)]
+            any_changed = int(any(w != e for w, e in zip(wants, entries)))
+            entries = wants
+        else:
+            any_changed = max(all_gather_i64(changed))
         if not any_changed:
             if finish is not None:
                 payload = finish()
@@ -106,14 +116,21 @@ def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, firs
 
 
 def torch_all_gather_i64(group=None, device=None):
-    """all_gather of one int64 per rank with torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    """all_gather of one int64 per rank with torch.distributed (NCCL on GPUs, gloo on CPU): one collective
+    into a preallocated tensor, one device-to-host read."""
     import torch
     import torch.distributed as dist
+    world = dist.get_world_size(group)
+    src = torch.zeros(1, dtype=torch.int64, device=device)
+    dst = torch.zeros(world, dtype=torch.int64, device=device)
 
     def fn(v):
-        t = torch.tensor([int(v)], dtype=torch.int64, device=device)
-        out = [torch.zeros_like(t) for _ in range(dist.get_world_size(group))]
-        dist.all_gather(out, t, group=group)
+        src.fill_(int(v))
+        if hasattr(dist, "all_gather_into_tensor") and (device is not None and str(device).startswith("cuda")):
+            dist.all_gather_into_tensor(dst, src, group=group)
+            return dst.tolist()
+        out = [torch.zeros_like(src) for _ in range(world)]
+        dist.all_gather(out, src, group=group)
         return [int(x.item()) for x in out]
     return fn
 

@@ -64,6 +64,17 @@ def _worker(rank, world, port, total_len, q):
         recs = _records_for_shard(o, buf, sh)
         gather = rd.torch_all_gather_i64()
         entry, exit_cur, payload, rounds = rd.resolve_cursor_chain(lambda e: _replay_tdfa(recs, e, total_len), rank, world, sh.start, gather)
+        # the bench's variant: replay-only rounds, one collective per round (every rank knows all shard starts),
+        # output produced once at the end -- must settle on the same cursors and the same records
+        last = {}
+
+        def replay_only(e):
+            last["exit"], last["out"] = _replay_tdfa(recs, e, total_len)
+            return last["exit"], None
+        starts = [rd.shard_buffer(total_len, world, r, halo=4096, align=4096).start for r in range(world)]
+        entry2, exit2, payload2, rounds2 = rd.resolve_cursor_chain(replay_only, rank, world, sh.start, gather, finish=lambda: last["out"],
+                                                                   all_starts=starts)
+        assert (entry2, exit2, payload2) == (entry, exit_cur, payload) and rounds2 == rounds
         n_local = sum(k for _, _, k in payload)
         counts = gather(n_local)
         q.put((rank, entry, exit_cur, n_local, [(s, e, k) for s, e, k in payload][:3], rounds, counts))
