@@ -372,16 +372,16 @@ __device__ inline int thompson_match(const DevMeta& m, const uint32_t* __restric
     }
     return (cur & accept) != 0;
   }
-  for (int64_t ss = 0; ss <= l; ss++) {
-    cur = start_closure;
+  // The generated code restarts the simulation from every searchStart (thompson.go:69-131), O(l^2) when nothing
+  // matches.  Its step is union-linear -- next = OR over the live states of a per-state, position-independent
+  // closure mask -- so the union over all starts of "states alive at offset off" is one simulation that re-adds
+  // the start closure at every offset, and "some start reaches an accepting state" is the same boolean.
+  cur = start_closure;
+  for (int64_t off = 0; off < l; off++) {
     if (cur & accept) return 1;
-    for (int64_t off = ss; off < l; off++) {
-      cur = thompson_step(m, img, cur, char_mask, in[off]);
-      if (cur == 0) break;
-      if (cur & accept) return 1;
-    }
+    cur = thompson_step(m, img, cur, char_mask, in[off]) | start_closure;
   }
-  return 0;
+  return (cur & accept) != 0;
 }
 
 // One start position of the TDFA walk (tdfa.go:905-994).  `in`/`l` is the slice FindBytes sees,

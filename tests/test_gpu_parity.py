@@ -276,3 +276,58 @@ def test_find_all_host_buffer_pipelined_upload():
         check_find_all(p2, o2, synth.make_buffer("log", synth.BLOCK + 17))
     finally:
         _lib.check(L.rgx_ctx_set_chunk_bytes(ctx, 256 << 20))
+
+
+def test_find_all_at_scale_properties():
+    """Larger buffers than the oracle can check everywhere: (1) 32 MiB of each bench workload against the
+    oracle, bit for bit; (2) 256 MiB of the URL workload three ways -- one device call, three shards chained
+    through their exit cursors, and the pipelined host-buffer call with 16 MiB chunks -- must give identical
+    records and repeat counts (the cursor replay crosses every shard / chunk boundary)."""
+    import ctypes as C
+    import torch
+    from regengo_b200 import _lib
+    from regengo_b200 import dist as rd
+    for kind, pat in (("url", synth.URL_PATTERN), ("log", synth.EMAIL_PATTERN)):
+        p, o = pair(pat)
+        buf = synth.make_buffer(kind, 32 * synth.BLOCK + 4321, first_block=1000)
+        assert check_find_all(p, o, buf) > 50000
+    p, _ = pair(synth.URL_PATTERN)
+    L = _lib.load()
+    ctx = rg.context(0)
+    total = 256 * synth.BLOCK + 12345
+    dbuf = synth.make_buffer("url", total, first_block=5000, device=torch.device("cuda", 0))
+    nc = p.num_cap
+    cap = total // 64
+    d_out = torch.empty(cap * nc, dtype=torch.int64, device="cuda")
+    d_reps = torch.empty(cap, dtype=torch.int32, device="cuda")
+    n_rec = C.c_uint64()
+    tot = _lib.check(L.rgx_find_all_dev(ctx, p._h, dbuf.data_ptr(), total, -1, d_out.data_ptr(), d_reps.data_ptr(), cap, C.byref(n_rec)))
+    torch.cuda.synchronize()
+    ref_recs = d_out[: n_rec.value * nc].clone()
+    ref_reps = d_reps[: n_rec.value].clone()
+    assert int(ref_reps.sum().item()) == tot and n_rec.value > 500000
+    # three shards, exit cursor of one is the entry of the next
+    entry, got_recs, got_reps, got_tot = 0, [], [], 0
+    for r in range(3):
+        sh = rd.shard_buffer(total, 3, r, halo=1 << 20)
+        n2, exit_cur = C.c_uint64(), C.c_int64()
+        t2 = _lib.check(L.rgx_find_all_shard_dev(ctx, p._h, dbuf.data_ptr() + sh.start, sh.buf_len, sh.shard_len, int(sh.is_last),
+                                                 entry - sh.start, sh.start, 0, d_out.data_ptr(), d_reps.data_ptr(), cap,
+                                                 C.byref(n2), C.byref(exit_cur)))
+        torch.cuda.synchronize()
+        got_recs.append(d_out[: n2.value * nc].clone()); got_reps.append(d_reps[: n2.value].clone()); got_tot += t2
+        entry = sh.start + exit_cur.value
+    assert got_tot == tot
+    assert torch.equal(torch.cat(got_recs), ref_recs) and torch.equal(torch.cat(got_reps), ref_reps)
+    # pipelined host-buffer call
+    host = dbuf.cpu().numpy()
+    h_out = np.empty(cap * nc, dtype=np.int64)
+    h_reps = np.empty(cap, dtype=np.uint32)
+    _lib.check(L.rgx_ctx_set_chunk_bytes(ctx, 16 << 20))
+    try:
+        t3 = _lib.check(L.rgx_find_all_rle(ctx, p._h, host.ctypes.data, total, -1, h_out.ctypes.data, h_reps.ctypes.data, cap, C.byref(n_rec)))
+    finally:
+        _lib.check(L.rgx_ctx_set_chunk_bytes(ctx, 256 << 20))
+    assert t3 == tot and n_rec.value == ref_reps.numel()
+    assert np.array_equal(h_out[: n_rec.value * nc], ref_recs.cpu().numpy())
+    assert np.array_equal(h_reps[: n_rec.value].astype(np.int64), ref_reps.cpu().numpy().astype(np.int64))
