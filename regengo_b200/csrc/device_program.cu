@@ -271,6 +271,57 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     if ((P.class_bits[(size_t)L * 8 + (b >> 5)] >> (b & 31)) & 1u) continue;
     w[m.off_inst + 4 * i] |= (uint32_t)IF_ATOMIC_LOOP << 8;
   }
+  // Straight-line whole program?  (captures and nops between single-byte steps, then Match)
+  if (P.find_engine == FIND_BT && m.n_alt == 0 && m.n_empty == 0) {
+    std::vector<Bits256> classes;
+    std::vector<uint8_t> steps;
+    int pc = prog.start;
+    bool ok = true, done = false;
+    size_t guard = 0;
+    while (ok && !done && guard++ <= n) {
+      const Inst& in = prog.inst[pc];
+      Bits256 set;
+      bool consumes = false;
+      switch (in.op) {
+        case InstNop: case InstCapture: pc = (int)in.out; break;
+        case InstRune1:
+          if (in.rune.size() != 1 || in.rune[0] >= 128) { ok = false; break; }
+          set.set((uint32_t)in.rune[0]); consumes = true; break;
+        case InstRune:
+          if (P.unicode_class[pc]) { ok = false; break; }
+          for (int k = 0; k < 8; k++) set.w[k] = P.class_bits[(size_t)pc * 8 + k];
+          if (set.w[4] | set.w[5] | set.w[6] | set.w[7]) { ok = false; break; }   // ASCII sets only
+          consumes = true; break;
+        case InstMatch: done = true; break;
+        default: ok = false; break;
+      }
+      if (ok && consumes) {
+        size_t k = 0;
+        for (; k < classes.size(); k++) if (std::memcmp(classes[k].w, set.w, sizeof(set.w)) == 0) break;
+        if (k == classes.size()) classes.push_back(set);
+        if (classes.size() > 8 || steps.size() >= 32) { ok = false; break; }
+        steps.push_back((uint8_t)k);
+        pc = (int)in.out;
+      }
+    }
+    if (ok && done && !steps.empty()) {
+      m.sl_n = (int32_t)steps.size();
+      m.sl_ncls = (int32_t)classes.size();
+      for (size_t i = 0; i < steps.size(); i++) m.sl_cls[i] = steps[i];
+      m.off_sl_cm = (uint32_t)w.size();
+      for (uint32_t c0 = 0; c0 < 256; c0 += 4) {
+        uint32_t word = 0;
+        for (uint32_t j = 0; j < 4; j++) {
+          const uint32_t c = c0 + j;
+          uint32_t bits = 0;
+          for (size_t k = 0; k < classes.size(); k++) if ((classes[k].w[c >> 5] >> (c & 31)) & 1u) bits |= 1u << k;
+          word |= bits << (8 * j);
+        }
+        w.push_back(word);
+      }
+      align4();
+    }
+  }
   m.image_words = (uint32_t)w.size();
 
   // Recognise  (cap|nop)* C+ (cap|nop)* b ...  (greedy loop over an ASCII class C, then a literal byte

@@ -62,6 +62,13 @@ struct DevMeta {
   // greedy one -- and is evaluated directly instead of by the goto-machine: lin[i] = kind | arg << 8.
   int32_t lin_n;               // 0: not linear
   uint32_t lin[40];
+  // Straight-line WHOLE program (no Alt, no EmptyWidth): step i consumes one byte of class sl_cls[i]; the
+  // classes are de-duplicated (<= 8) and cm[c] (256 bytes at off_sl_cm) has bit k set iff byte c is in class k.
+  // Lets the FindReader attempt table be computed bit-parallel (kernels_stream.cuh).
+  int32_t sl_n;                // 0: not straight-line
+  int32_t sl_ncls;
+  uint32_t off_sl_cm;
+  uint8_t sl_cls[32];
 };
 
 struct DeviceImage {

@@ -199,6 +199,110 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
   }
 }
 
+// The same table for a STRAIGHT-LINE program (device_program.cu: sl_*), bit-parallel: a thread owns 64
+// positions; for each byte class one bit mask over its 64 + S - 1 bytes; "the attempt at position j survives
+// step i" is bit j of AND_i (mask[class_i] >> i); the number of steps survived (= failure offset - start) is
+// counted in bit planes.  No interpreter, no divergence.
+__global__ void __launch_bounds__(256) find_reader_table_linear_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
+                                                                       const uint8_t* __restrict__ d_stream, const uint64_t len,
+                                                                       uint16_t* __restrict__ table) {
+  extern __shared__ __align__(16) uint32_t smem_img[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const uint32_t* img = gimg;
+  if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
+  const uint8_t* cm = reinterpret_cast<const uint8_t*>(img + m.off_sl_cm);
+  const int S = m.sl_n, ncls = m.sl_ncls;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t n_units = (len + 63) / 64;
+  const bool aligned = ((uintptr_t)d_stream & 15u) == 0;
+  for (uint64_t u = tid; u < n_units; u += stride) {
+    const uint64_t p0 = u * 64;
+    const uint32_t nb = (uint32_t)min((uint64_t)64, len - p0);
+    // class bits of my 96 bytes (bytes past the end read as 0xFF: in no ASCII class)
+    uint32_t bw[24];
+    if (aligned && p0 + 96 <= len) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(d_stream + p0 + 16 * q);
+        bw[4 * q] = v.x; bw[4 * q + 1] = v.y; bw[4 * q + 2] = v.z; bw[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 24; q++) {
+        uint32_t x = 0;
+        for (int b = 0; b < 4; b++) {
+          const uint64_t pp = p0 + 4 * q + b;
+          x |= (uint32_t)(pp < len ? d_stream[pp] : 0xFFu) << (8 * b);
+        }
+        bw[q] = x;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 24; q++) {
+      const uint32_t x = bw[q];
+      bw[q] = (uint32_t)cm[x & 255u] | ((uint32_t)cm[(x >> 8) & 255u] << 8) | ((uint32_t)cm[(x >> 16) & 255u] << 16) |
+              ((uint32_t)cm[x >> 24] << 24);
+    }
+    // per class: a 96-bit mask (lo: positions 0..63, hi: 64..95)
+    unsigned long long mlo[8];
+    uint32_t mhi[8];
+    for (int k = 0; k < ncls; k++) {
+      unsigned long long lo = 0;
+      uint32_t hi = 0;
+#pragma unroll
+      for (int q = 0; q < 24; q++) {
+        const uint32_t t = (bw[q] >> k) & 0x01010101u;                    // bit 0 of each byte
+        const uint32_t nib = ((t * 0x10204080u) >> 28) & 0xFu;            // -> 4 consecutive bits, byte 0 lowest
+        if (q < 16) lo |= (unsigned long long)nib << (4 * q); else hi |= nib << (4 * (q - 16));
+      }
+      mlo[k] = lo; mhi[k] = hi;
+    }
+    // survive steps
+    unsigned long long alive = ~0ull, cand = 0;
+    unsigned long long pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, pl4 = 0, pl5 = 0;     // steps survived, bit-sliced (S <= 32)
+    for (int i = 0; i < S; i++) {
+      const int k = m.sl_cls[i];
+      const unsigned long long sh = i == 0 ? mlo[k] : ((mlo[k] >> i) | ((unsigned long long)mhi[k] << (64 - i)));
+      alive &= sh;
+      if (i == 0) cand = alive;
+      unsigned long long carry = alive, t;
+      t = pl0 & carry; pl0 ^= carry; carry = t;
+      t = pl1 & carry; pl1 ^= carry; carry = t;
+      t = pl2 & carry; pl2 ^= carry; carry = t;
+      t = pl3 & carry; pl3 ^= carry; carry = t;
+      t = pl4 & carry; pl4 ^= carry; carry = t;
+      pl5 ^= carry;
+    }
+    // entries (16 bytes = 8 entries per store when the unit is whole: a 2-byte store per position would touch
+    // one sector per lane and position)
+    auto entry_of = [&](const uint32_t j) -> uint32_t {
+      if (!((cand >> j) & 1ull)) {
+        const unsigned long long rest = j + 1 < 64 ? cand >> (j + 1) : 0ull;
+        uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : 64u - j;
+        if (j + dist > nb) dist = nb - j;
+        return (1u << 8) | dist;
+      }
+      const uint32_t cnt = (uint32_t)((pl0 >> j) & 1ull) | ((uint32_t)((pl1 >> j) & 1ull) << 1) | ((uint32_t)((pl2 >> j) & 1ull) << 2) |
+                           ((uint32_t)((pl3 >> j) & 1ull) << 3) | ((uint32_t)((pl4 >> j) & 1ull) << 4) | ((uint32_t)((pl5 >> j) & 1ull) << 5);
+      if (cnt == (uint32_t)S) return 0x8000u | ((uint32_t)S << 8) | (uint32_t)S;
+      return ((cnt + 1u) << 8) | (cnt + 1u);
+    };
+    if (nb == 64 && (((uintptr_t)(table + p0)) & 15u) == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint4 v;
+        v.x = entry_of(8 * q) | (entry_of(8 * q + 1) << 16);
+        v.y = entry_of(8 * q + 2) | (entry_of(8 * q + 3) << 16);
+        v.z = entry_of(8 * q + 4) | (entry_of(8 * q + 5) << 16);
+        v.w = entry_of(8 * q + 6) | (entry_of(8 * q + 7) << 16);
+        *reinterpret_cast<uint4*>(table + p0 + 8 * q) = v;
+      }
+    } else {
+      for (uint32_t j = 0; j < nb; j++) table[p0 + j] = (uint16_t)entry_of(j);
+    }
+  }
+}
+
 struct ReaderHit { long long search_abs; uint32_t d_true, d_text; unsigned long long chunk; };   // stream offset of searchPos; attempt start / text position relative to it; ChunkIndex
 
 // bytes.Index(hay[from:], hay[ns:ns+nl]) by a whole warp: lane i tests from + i, from + 32 + i, ...
