@@ -318,7 +318,9 @@ __device__ __forceinline__ int64_t warp_index_of_text(const uint8_t* hay, int64_
   return ns;
 }
 
-// MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].
+// MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].  MODE 2: one pass -- list the hits of chunk j
+// at j * region (a chunk cannot hold more than `region` matches) and count them; a chunk that would overflow
+// its region sets ERR_SLAB and the caller falls back to the two-pass form.
 // One WARP per chunk.  The replay is sequential, but its memory accesses are not: the lanes fetch 32 table
 // entries at a time (one coalesced load) and the attempt chain is followed through them with shuffles; the
 // bytes.Index scan tests 32 positions per step.  All control flow is warp-uniform.
@@ -345,7 +347,8 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
     const uint16_t* tab = table + (cstart - base_off);
     const int64_t data_len = (int64_t)dlen;
     int64_t pos = 0;
-    unsigned long long n = 0, w = MODE == 1 ? bases[j] : 0;
+    unsigned long long n = 0, w = MODE == 1 ? bases[j] : MODE == 2 ? j * cap : 0;
+    const unsigned long long wend = MODE == 2 ? w + cap : cap;
     bool stop = false;
     while (!stop && pos < data_len) {
       // FindBytesReuse(chunk[pos:data_len]): attempts at pos, f+1, ...
@@ -374,7 +377,8 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
       const int64_t mstart = warp_index_of_text(chunk, pos, a, mlen, lane);
       const int64_t mend = mstart + mlen;
       if (full && mend > data_len - (int64_t)cp.L) break;  // too close to the boundary: next chunk's job
-      if (MODE == 1 && w < cap && lane == 0) {
+      if (MODE == 2 && w >= wend) { if (lane == 0) atomicOr(err, ERR_SLAB); break; }
+      if (MODE != 0 && w < wend && lane == 0) {
         ReaderHit h;
         h.search_abs = (long long)cstart + pos; h.d_true = (uint32_t)(a - pos); h.d_text = (uint32_t)(mstart - pos); h.chunk = k;
         hits[w] = h;
@@ -382,13 +386,16 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
       w++; n++;
       if (mlen > 0) pos = mend; else pos++;
     }
-    if (MODE == 0 && lane == 0) counts[j] = n;
+    if (MODE != 1 && lane == 0) counts[j] = n;
   }
 }
 
 __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                   const uint8_t* __restrict__ d_stream, const uint64_t base_off,
                                                                   const ChunkPlan cp, const ReaderHit* __restrict__ hits, const uint64_t n_hits,
+                                                                  const uint64_t region, const uint64_t n_run,
+                                                                  const unsigned long long* __restrict__ counts,
+                                                                  const unsigned long long* __restrict__ bases,
                                                                   int64_t* __restrict__ out_soff, int32_t* __restrict__ out_chunk,
                                                                   int64_t* __restrict__ out_rec, const ScratchPlan sp, int* err) {
   extern __shared__ __align__(16) uint32_t smem_img[];
@@ -397,6 +404,35 @@ __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta 
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
   const int nc = m.num_cap;
+  // region == 0: hits[0:n_hits) is the compact list.  region > 0: chunk j's hits sit at hits[j*region ...) and go
+  // to output positions bases[j] ...; a warp takes a chunk.
+  if (region > 0) {
+    const int lane = threadIdx.x & 31;
+    for (uint64_t j = sc.tid >> 5; j < n_run; j += sp.stride >> 5) {
+      const unsigned long long cnt = counts[j], ob = bases[j];
+      for (unsigned long long t = lane; t < cnt; t += 32) {
+        const unsigned long long i = ob + t;
+        if (i >= n_hits) break;
+        const ReaderHit h = hits[j * region + t];
+        const uint64_t k = h.chunk;
+        uint64_t cstart, dlen;
+        bool full;
+        chunk_geometry(cp, k, cstart, dlen, full);
+        (void)full;
+        const int64_t pos = h.search_abs - (long long)cstart;
+        const uint8_t* slice = d_stream + ((uint64_t)h.search_abs - base_off);
+        const int64_t sl = (int64_t)dlen - pos;
+        int32_t caps[MAX_CAPS];
+        int64_t rec[MAX_CAPS];
+        bt_machine<MODE_FINDALL>(m, img, slice, sl, (int64_t)h.d_true, caps, sc, err);
+        bt_emit_record(caps, nc, (int64_t)h.d_true, sl, 0, rec);
+        out_soff[i] = h.search_abs + (long long)h.d_text;
+        out_chunk[i] = (int32_t)k;
+        for (int g = 0; g < nc; g++) out_rec[i * nc + g] = rec[g] < 0 ? -1 : h.search_abs + rec[g];
+      }
+    }
+    return;
+  }
   for (uint64_t i = sc.tid; i < n_hits; i += sp.stride) {
     const ReaderHit h = hits[i];
     const uint64_t k = h.chunk;
