@@ -14,7 +14,6 @@
 namespace rgx {
 
 static const int32_t MaxRune = 0x10FFFF;
-static const int32_t RuneError = 0xFFFD;
 
 // ---------------------------------------------------------------------------------------
 // UTF-8 decode of the pattern text (Go: nextRune / utf8.DecodeRuneInString).
@@ -109,14 +108,12 @@ static void clean_class(std::vector<int32_t>& r) {
 
 static void negate_class(std::vector<int32_t>& r) {
   int32_t next_lo = 0;
-  size_t w = 0;
   std::vector<int32_t> out;
   for (size_t i = 0; i < r.size(); i += 2) {
     int32_t lo = r[i], hi = r[i + 1];
     if (next_lo <= lo - 1) { out.push_back(next_lo); out.push_back(lo - 1); }
     next_lo = hi + 1;
   }
-  (void)w;
   if (next_lo <= MaxRune) { out.push_back(next_lo); out.push_back(MaxRune); }
   r.swap(out);
 }
