@@ -248,6 +248,9 @@ def test_fast_scan_prefix_boundaries(pattern, lit):
     check_find_all(p, o, bytes(buf))
     check_find_all(p, o, bytes(buf[: n - 1]))
     check_find_all(p, o, bytes(buf[5: 40000]))
+    check_find_all(p, o, bytes(buf[: 65536]))        # ends exactly on a segment boundary
+    check_find_all(p, o, bytes(buf[: 32768]))
+    check_find_all(p, o, bytes(buf[: 32768 + 3]))
     check_find_all(p, o, lit)
     check_find_all(p, o, tok)
     check_find_all(p, o, (tok + b" ") * 3000)       # dense: every lane has several hits
