@@ -153,6 +153,45 @@ __device__ __forceinline__ Scratch scratch_of(const ScratchPlan& sp) {
   return sc;
 }
 
+// One TDFA start without tags (tdfa.go:937-975 minus the tag bookkeeping): last accepting offset or -1, and the
+// reach (one past the byte that stopped the walk; l + 1 when the walk ran into the end of the input, because
+// then the outcome may depend on l).  For tables without end-of-text accepts and with one start state.
+__device__ __forceinline__ int64_t tdfa_walk_light(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* __restrict__ in,
+                                                   const int64_t l, const int64_t start, int64_t* reach) {
+  const uint32_t* trans = img + m.off_t_trans;
+  const uint32_t* acc = img + m.off_t_accept;
+  uint32_t state = (uint32_t)m.t_start_any;
+  int64_t match_end = -1;
+  for (int64_t i = start; i < l; i++) {
+    const uint32_t c = in[i];
+    if (c >= 128) { *reach = i + 1; return match_end; }
+    const uint32_t nx = trans[state * 128 + c] & 0xFFFFu;
+    if (nx == TDFA_NONE) { *reach = i + 1; return match_end; }
+    state = nx;
+    if (acc[state] & 1u) match_end = i + 1;
+  }
+  *reach = l + 1;
+  return match_end;
+}
+
+// One attempt at position s of in[0:l): 1 = match (*mlen), 0 = fail (*next_start = where FindBytes tries next:
+// failure offset + 1 for the goto-machine, s + 1 for the TDFA, which tries every start).
+__device__ __forceinline__ int reader_attempt(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* __restrict__ in,
+                                              const int64_t l, const int64_t s, const Scratch& sc, int* err, int64_t* mlen,
+                                              int64_t* next_start, int64_t* reach) {
+  if (m.find_engine == FIND_TDFA) {
+    const int64_t me = tdfa_walk_light(m, img, in, l, s, reach);
+    if (me >= 0) { *mlen = me - s; return 1; }
+    *next_start = s + 1;
+    return 0;
+  }
+  int32_t caps[MAX_CAPS];
+  int64_t f = 0;
+  if (bt_machine<MODE_FINDALL, true>(m, img, in, l, s, caps, sc, err, -1, 0, 0, &f, reach)) { *mlen = caps[1]; return 1; }
+  *next_start = f + 1;
+  return 0;
+}
+
 // d_stream[0:len) = the shard; entry i describes the attempt at shard position i with the whole shard visible
 __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                 const uint8_t* __restrict__ d_stream, const uint64_t len,
@@ -180,17 +219,15 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
         const uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : nb - j;   // next candidate, or my last byte + 1
         entry = (1u << 8) | dist;                                                  // reach 1, next = dist (<= 64)
       } else {
-        int32_t caps[MAX_CAPS];
-        int64_t f = 0, reach = 0;
+        int64_t ml = 0, ns = 0, reach = 0;
         const int64_t s = (int64_t)(p0 + j);
-        const int ok = bt_machine<MODE_FINDALL, true>(m, img, d_stream, (int64_t)len, s, caps, sc, err, -1, 0, 0, &f, &reach);
+        const int ok = reader_attempt(m, img, d_stream, (int64_t)len, s, sc, err, &ml, &ns, &reach);
         const int64_t rr = reach - s;
         const uint32_t r7 = rr >= (int64_t)RT_SLOW_REACH || rr < 1 ? RT_SLOW_REACH : (uint32_t)rr;
         if (ok) {
-          const int64_t ml = caps[1];
           entry = 0x8000u | (r7 << 8) | (ml >= (int64_t)RT_SLOW_VAL || ml < 0 ? RT_SLOW_VAL : (uint32_t)ml);
         } else {
-          const int64_t nx = f + 1 - s;
+          const int64_t nx = ns - s;
           entry = (r7 << 8) | (nx >= (int64_t)RT_SLOW_VAL || nx < 1 ? RT_SLOW_VAL : (uint32_t)nx);
         }
       }
@@ -366,11 +403,10 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
           if (e & 0x8000u) { mlen = (int64_t)v; break; }
           a += (int64_t)v;
         } else {
-          int32_t caps[MAX_CAPS];
-          int64_t f = 0, reach = 0;
-          if (bt_machine<MODE_FINDALL, true>(m, img, chunk, data_len, a, caps, sc, err, -1, 0, 0, &f, &reach)) { mlen = caps[1]; break; }
-          if (f >= data_len) { a = data_len; break; }   // `if l > offset` fails: FindBytesReuse returns false
-          a = f + 1;
+          int64_t ml = 0, ns = 0, reach = 0;
+          if (reader_attempt(m, img, chunk, data_len, a, sc, err, &ml, &ns, &reach)) { mlen = ml; break; }
+          if (ns > data_len) { a = data_len; break; }   // goto-machine: `if l > offset` fails, FindBytesReuse returns false
+          a = ns;
         }
       }
       if (mlen < 0) break;
@@ -390,6 +426,25 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
   }
 }
 
+// Offset record (slice-relative) of the attempt at `start` of slice[0:sl), known to match.
+__device__ __forceinline__ void reader_record(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* __restrict__ slice,
+                                              const int64_t sl, const int64_t start, const int nc, const Scratch& sc, int* err,
+                                              int64_t* rec) {
+  if (m.find_engine == FIND_TDFA) {
+    int64_t mtags[MAX_CAPS];
+    tdfa_walk(m, img, slice, sl, start, start == 0, mtags);
+    rec[0] = mtags[0]; rec[1] = mtags[1];
+    for (int g = 1; g < nc / 2; g++) {
+      if (mtags[2 * g] >= 0) { rec[2 * g] = mtags[2 * g]; rec[2 * g + 1] = mtags[2 * g + 1]; }
+      else { rec[2 * g] = -1; rec[2 * g + 1] = -1; }
+    }
+    return;
+  }
+  int32_t caps[MAX_CAPS];
+  bt_machine<MODE_FINDALL>(m, img, slice, sl, start, caps, sc, err);
+  bt_emit_record(caps, nc, start, sl, 0, rec);
+}
+
 __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                   const uint8_t* __restrict__ d_stream, const uint64_t base_off,
                                                                   const ChunkPlan cp, const ReaderHit* __restrict__ hits, const uint64_t n_hits,
@@ -403,7 +458,7 @@ __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta 
   const uint32_t* img = gimg;
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
-  const int nc = m.num_cap;
+  const int nc = m.find_engine == FIND_TDFA ? m.t_ntags : m.num_cap;
   // region == 0: hits[0:n_hits) is the compact list.  region > 0: chunk j's hits sit at hits[j*region ...) and go
   // to output positions bases[j] ...; a warp takes a chunk.
   if (region > 0) {
@@ -422,10 +477,8 @@ __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta 
         const int64_t pos = h.search_abs - (long long)cstart;
         const uint8_t* slice = d_stream + ((uint64_t)h.search_abs - base_off);
         const int64_t sl = (int64_t)dlen - pos;
-        int32_t caps[MAX_CAPS];
         int64_t rec[MAX_CAPS];
-        bt_machine<MODE_FINDALL>(m, img, slice, sl, (int64_t)h.d_true, caps, sc, err);
-        bt_emit_record(caps, nc, (int64_t)h.d_true, sl, 0, rec);
+        reader_record(m, img, slice, sl, (int64_t)h.d_true, nc, sc, err, rec);
         out_soff[i] = h.search_abs + (long long)h.d_text;
         out_chunk[i] = (int32_t)k;
         for (int g = 0; g < nc; g++) out_rec[i * nc + g] = rec[g] < 0 ? -1 : h.search_abs + rec[g];
@@ -443,10 +496,8 @@ __global__ void __launch_bounds__(128) find_reader_records_kernel(const DevMeta 
     const int64_t pos = h.search_abs - (long long)cstart;
     const uint8_t* slice = d_stream + ((uint64_t)h.search_abs - base_off);
     const int64_t sl = (int64_t)dlen - pos;
-    int32_t caps[MAX_CAPS];
     int64_t rec[MAX_CAPS];
-    bt_machine<MODE_FINDALL>(m, img, slice, sl, (int64_t)h.d_true, caps, sc, err);
-    bt_emit_record(caps, nc, (int64_t)h.d_true, sl, 0, rec);
+    reader_record(m, img, slice, sl, (int64_t)h.d_true, nc, sc, err, rec);
     out_soff[i] = h.search_abs + (long long)h.d_text;
     out_chunk[i] = (int32_t)k;
     for (int g = 0; g < nc; g++) out_rec[i * nc + g] = rec[g] < 0 ? -1 : h.search_abs + rec[g];

@@ -82,29 +82,31 @@ def main():
                       "slowest": [{"ms": round(m, 3), "pattern": q, "engine": e, "bytes": b} for m, q, e, b in slowest[:5]]}), flush=True)
 
     # ---- C5: FindReader over a device-resident stream, default 64 KiB buffer and 1 MiB buffer
-    p = rg.Pattern(synth.DATE_CAPTURE_PATTERN)
     n_bytes = int(args.stream_gib * (1 << 30))
-    buf = synth.make_buffer("stream", n_bytes, device=dev, digit_noise=0.02)
-    cap = n_bytes // 40
-    nc = p.num_cap
-    d_so = torch.empty(cap, dtype=torch.int64, device=dev)
-    d_ci = torch.empty(cap, dtype=torch.int32, device=dev)
-    d_rec = torch.empty(cap * nc, dtype=torch.int64, device=dev)
-    for bsz in (0, 1 << 20):
-        def call():
-            return _lib.check(L.rgx_find_reader_dev(ctx, p._h, buf.data_ptr(), 0, n_bytes, n_bytes, bsz, 0, 0, -1,
-                                                    d_so.data_ptr(), d_ci.data_ptr(), d_rec.data_ptr(), cap))
-        cnt = call()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(3):
-            call()
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
-        print(json.dumps({"measure": "C5 FindReader (rgx_find_reader_dev), DatePattern, device-resident stream",
-                          "buffer_size": bsz or 65536, "stream_bytes": n_bytes, "matches": int(cnt), "ms": ms,
-                          "GBps": n_bytes / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": n_bytes / (ms * 1e-3) / 1e9 / peak}), flush=True)
+    for name, pattern, kind, kw, sizes in (("DatePattern", synth.DATE_CAPTURE_PATTERN, "stream", dict(digit_noise=0.02), (0, 1 << 20)),
+                                           ("URLCapture (TDFA)", synth.URL_PATTERN, "url", {}, (0,))):
+      p = rg.Pattern(pattern)
+      buf = synth.make_buffer(kind, n_bytes, device=dev, **kw)
+      cap = n_bytes // 40
+      nc = p.num_cap
+      d_so = torch.empty(cap, dtype=torch.int64, device=dev)
+      d_ci = torch.empty(cap, dtype=torch.int32, device=dev)
+      d_rec = torch.empty(cap * nc, dtype=torch.int64, device=dev)
+      for bsz in sizes:
+          def call():
+              return _lib.check(L.rgx_find_reader_dev(ctx, p._h, buf.data_ptr(), 0, n_bytes, n_bytes, bsz, 0, 0, -1,
+                                                      d_so.data_ptr(), d_ci.data_ptr(), d_rec.data_ptr(), cap))
+          cnt = call()
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record(stream)
+          for _ in range(3):
+              call()
+          e1.record(stream)
+          torch.cuda.synchronize()
+          ms = e0.elapsed_time(e1) / 3
+          print(json.dumps({"measure": "C5 FindReader (rgx_find_reader_dev), " + name + ", device-resident stream",
+                            "buffer_size": bsz or 65536, "stream_bytes": n_bytes, "matches": int(cnt), "ms": ms,
+                            "GBps": n_bytes / (ms * 1e-3) / 1e9, "frac_of_measured_hbm": n_bytes / (ms * 1e-3) / 1e9 / peak}), flush=True)
 
 
 if __name__ == "__main__":
