@@ -206,32 +206,64 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
   for (uint64_t u = sc.tid; u < n_units; u += sp.stride) {
     const uint64_t p0 = u * 64;
     const uint32_t nb = (uint32_t)min((uint64_t)64, len - p0);
-    // which of my bytes can start a match
+    // which of my bytes can start a match (16-byte loads when the unit is whole and aligned)
     unsigned long long cand = 0;
-    for (uint32_t j = 0; j < nb; j++) {
-      const uint32_t c = d_stream[p0 + j];
-      if ((first[c >> 5] >> (c & 31)) & 1u) cand |= 1ull << j;
-    }
-    for (uint32_t j = 0; j < nb; j++) {
-      uint32_t entry;
-      if (!((cand >> j) & 1ull)) {
-        const unsigned long long rest = j + 1 < 64 ? cand >> (j + 1) : 0ull;
-        const uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : nb - j;   // next candidate, or my last byte + 1
-        entry = (1u << 8) | dist;                                                  // reach 1, next = dist (<= 64)
-      } else {
-        int64_t ml = 0, ns = 0, reach = 0;
-        const int64_t s = (int64_t)(p0 + j);
-        const int ok = reader_attempt(m, img, d_stream, (int64_t)len, s, sc, err, &ml, &ns, &reach);
-        const int64_t rr = reach - s;
-        const uint32_t r7 = rr >= (int64_t)RT_SLOW_REACH || rr < 1 ? RT_SLOW_REACH : (uint32_t)rr;
-        if (ok) {
-          entry = 0x8000u | (r7 << 8) | (ml >= (int64_t)RT_SLOW_VAL || ml < 0 ? RT_SLOW_VAL : (uint32_t)ml);
-        } else {
-          const int64_t nx = ns - s;
-          entry = (r7 << 8) | (nx >= (int64_t)RT_SLOW_VAL || nx < 1 ? RT_SLOW_VAL : (uint32_t)nx);
+    const bool whole = nb == 64 && (((uintptr_t)(d_stream + p0)) & 15u) == 0;
+    if (whole) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(d_stream + p0 + 16 * q);
+        const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int b = 0; b < 16; b++) {
+          const uint32_t c = (ws[b >> 2] >> (8 * (b & 3))) & 255u;
+          cand |= (unsigned long long)((first[c >> 5] >> (c & 31)) & 1u) << (16 * q + b);
         }
       }
-      table[p0 + j] = (uint16_t)entry;
+    } else {
+      for (uint32_t j = 0; j < nb; j++) {
+        const uint32_t c = d_stream[p0 + j];
+        if ((first[c >> 5] >> (c & 31)) & 1u) cand |= 1ull << j;
+      }
+    }
+    // the attempts (one per candidate), kept in a small per-thread array
+    uint16_t ent[64];
+    for (unsigned long long rest = cand; rest;) {
+      const uint32_t j = (uint32_t)__ffsll((long long)rest) - 1;
+      rest &= rest - 1;
+      int64_t ml = 0, ns = 0, reach = 0;
+      const int64_t s = (int64_t)(p0 + j);
+      const int ok = reader_attempt(m, img, d_stream, (int64_t)len, s, sc, err, &ml, &ns, &reach);
+      const int64_t rr = reach - s;
+      const uint32_t r7 = rr >= (int64_t)RT_SLOW_REACH || rr < 1 ? RT_SLOW_REACH : (uint32_t)rr;
+      uint32_t entry;
+      if (ok) {
+        entry = 0x8000u | (r7 << 8) | (ml >= (int64_t)RT_SLOW_VAL || ml < 0 ? RT_SLOW_VAL : (uint32_t)ml);
+      } else {
+        const int64_t nx = ns - s;
+        entry = (r7 << 8) | (nx >= (int64_t)RT_SLOW_VAL || nx < 1 ? RT_SLOW_VAL : (uint32_t)nx);
+      }
+      ent[j] = (uint16_t)entry;
+    }
+    auto entry_of = [&](const uint32_t j) -> uint32_t {
+      if ((cand >> j) & 1ull) return ent[j];
+      const unsigned long long rest = j + 1 < 64 ? cand >> (j + 1) : 0ull;
+      uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : 64u - j;   // next candidate, or my last byte + 1
+      if (j + dist > nb) dist = nb - j;
+      return (1u << 8) | dist;                                                  // reach 1, next = dist (<= 64)
+    };
+    if (whole && (((uintptr_t)(table + p0)) & 15u) == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        uint4 v;
+        v.x = entry_of(8 * q) | (entry_of(8 * q + 1) << 16);
+        v.y = entry_of(8 * q + 2) | (entry_of(8 * q + 3) << 16);
+        v.z = entry_of(8 * q + 4) | (entry_of(8 * q + 5) << 16);
+        v.w = entry_of(8 * q + 6) | (entry_of(8 * q + 7) << 16);
+        *reinterpret_cast<uint4*>(table + p0 + 8 * q) = v;
+      }
+    } else {
+      for (uint32_t j = 0; j < nb; j++) table[p0 + j] = (uint16_t)entry_of(j);
     }
   }
 }
