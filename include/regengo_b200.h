@@ -80,6 +80,10 @@ void rgx_program_free(rgx_program* p);
 int rgx_program_info(const rgx_program* p, rgx_info* out);
 /* JSON dump of the program (Prog listing, masks, TDFA tables); the string lives as long as p. */
 const char* rgx_program_json(const rgx_program* p);
+/* JSON summary of how the device kernels will run the program (host computation, no GPU needed): image size,
+ * FindAll start filter and prefix skip, run-anchor shape, straight-line forms, FindReader path.  Written into
+ * buf (NUL-terminated) when cap suffices; returns the length needed (without the NUL). */
+int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap);
 /* Name of capture group i (1..k), "" if unnamed; NULL if out of range. */
 const char* rgx_program_group_name(const rgx_program* p, int32_t i);
 

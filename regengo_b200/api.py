@@ -188,6 +188,15 @@ class Pattern:
         found, rec = self.find_batch([data])
         return Result(data, rec[0], self.group_names) if found[0] else None
 
+    def device_plan(self):
+        """How the device kernels will run this pattern (host computation; dict)."""
+        import json as _json
+        L = _lib.load()
+        n = check(L.rgx_program_device_plan(self._h, None, 0))
+        buf = C.create_string_buffer(int(n) + 1)
+        check(L.rgx_program_device_plan(self._h, buf, int(n) + 1))
+        return _json.loads(buf.value.decode())
+
     # ---- FindAllBytes ----
     def find_all_offsets(self, data, n=-1):
         """FindAllBytes(data, n) as (count, int64[count, num_cap])."""

@@ -400,3 +400,38 @@ int rgx_find_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const
 
 #include "capi_findall.inc"
 #include "capi_stream.inc"
+
+extern "C" {
+
+int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
+  if (!p) { set_error("null argument"); return RGX_EINVAL; }
+  std::vector<uint32_t> words;
+  DevMeta m;
+  pack_program(p->prog, words, m);
+  std::string s = "{";
+  auto kv = [&](const char* k, long long v) { if (s.size() > 1) s += ", "; s += "\""; s += k; s += "\": "; s += std::to_string(v); };
+  kv("image_bytes", (long long)m.image_words * 4);
+  kv("find_engine", m.find_engine);
+  kv("gen_kind", m.gen_kind);
+  kv("prefix_len", m.prefix_len);
+  kv("nullable", m.nullable);
+  kv("fast_tdfa_scan", fast_tdfa_scan_ok(m) && parallel_findall_ok(m, p->prog) ? 1 : 0);
+  kv("parallel_findall", parallel_findall_ok(m, p->prog) ? 1 : 0);
+  kv("tdfa_skip_len", m.t_skip_len);
+  kv("tdfa_skip_state", m.t_skip_state);
+  kv("tdfa_prefix_events", m.t_pre_n);
+  kv("run_anchor", m.run_ok);
+  kv("run_literal", m.run_ok ? m.run_lit : -1);
+  kv("run_linear_elements", m.lin_n);
+  kv("straight_line_steps", m.sl_n);
+  kv("straight_line_classes", m.sl_ncls);
+  kv("n_alt", m.n_alt);
+  kv("n_empty", m.n_empty);
+  s += ", \"prefix\": \"";
+  for (int i = 0; i < m.prefix_len; i++) { char h[8]; std::snprintf(h, sizeof h, "%02x", m.prefix_bytes[i]); s += h; }
+  s += "\"}";
+  if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
+  return (int64_t)s.size();
+}
+
+}  // extern "C"
