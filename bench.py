@@ -310,12 +310,15 @@ def main():
     if not args.no_e2e:
         h_in = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
         h_in.copy_(buf[:n_bytes])
-        h_out = torch.empty(cap_rec * nc, dtype=torch.int64, pin_memory=True)
-        h_reps = torch.empty(cap_rec, dtype=torch.int32, pin_memory=True)
+        # result capacity: what the device-resident steps produced plus slack (a rank-local buffer holds about as
+        # many records as its shard did); keeps the pinned allocation near 1 GB per rank instead of 5
+        cap_e2e = min(cap_rec, int(n_rec.value) + int(n_rec.value) // 8 + 65536)
+        h_out = torch.empty(cap_e2e * nc, dtype=torch.int64, pin_memory=True)
+        h_reps = torch.empty(cap_e2e, dtype=torch.int32, pin_memory=True)
         torch.cuda.synchronize()
 
         def e2e_step():
-            return _lib.check(L.rgx_find_all_rle(ctx, pat._h, h_in.data_ptr(), n_bytes, -1, h_out.data_ptr(), h_reps.data_ptr(), cap_rec,
+            return _lib.check(L.rgx_find_all_rle(ctx, pat._h, h_in.data_ptr(), n_bytes, -1, h_out.data_ptr(), h_reps.data_ptr(), cap_e2e,
                                                  C.byref(n_rec)))
         k_e2e = max(3, min(args.steps, 5))
         e2e_step()
