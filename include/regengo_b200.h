@@ -84,6 +84,9 @@ const char* rgx_program_json(const rgx_program* p);
  * FindAll start filter and prefix skip, run-anchor shape, straight-line forms, FindReader path.  Written into
  * buf (NUL-terminated) when cap suffices; returns the length needed (without the NUL). */
 int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap);
+/* The packed device image (u32 words; the plan's w6_* entries are offsets into it).  Copies when cap_words suffices;
+ * returns the number of words.  Host computation; used by the packing tests. */
+int64_t rgx_program_device_image(const rgx_program* p, uint32_t* words_out, size_t cap_words);
 /* Name of capture group i (1..k), "" if unnamed; NULL if out of range. */
 const char* rgx_program_group_name(const rgx_program* p, int32_t i);
 

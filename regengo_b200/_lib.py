@@ -30,6 +30,7 @@ _SIGS = {
     "rgx_program_info": (C.c_int, [_P, C.POINTER(Info)]),
     "rgx_program_json": (C.c_char_p, [_P]),
     "rgx_program_device_plan": (C.c_int64, [_P, C.c_char_p, C.c_size_t]),
+    "rgx_program_device_image": (C.c_int64, [_P, _P, C.c_size_t]),
     "rgx_program_group_name": (C.c_char_p, [_P, C.c_int32]),
     "rgx_program_blob": (C.c_int64, [_P, _P, C.c_size_t]),
     "rgx_load": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),

@@ -197,6 +197,14 @@ class Pattern:
         check(L.rgx_program_device_plan(self._h, buf, int(n) + 1))
         return _json.loads(buf.value.decode())
 
+    def device_image(self):
+        """The packed device image (numpy uint32); device_plan()'s w6_* entries are offsets into it."""
+        L = _lib.load()
+        n = int(check(L.rgx_program_device_image(self._h, None, 0)))
+        words = np.empty(n, dtype=np.uint32)
+        check(L.rgx_program_device_image(self._h, words.ctypes.data, n))
+        return words
+
     # ---- FindAllBytes ----
     def find_all_offsets(self, data, n=-1):
         """FindAllBytes(data, n) as (count, int64[count, num_cap])."""

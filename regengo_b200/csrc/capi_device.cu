@@ -17,7 +17,7 @@
 #include "kernels_findall.cuh"
 #include "kernels_findall2.cuh"
 #include "kernels_chain.cuh"
-#include "kernels_scan5.cuh"
+#include "kernels_scan6.cuh"
 #include "kernels_emit.cuh"
 #include "kernels_btrun.cuh"
 #include "kernels_stream.cuh"
@@ -417,9 +417,14 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   kv("nullable", m.nullable);
   kv("fast_tdfa_scan", fast_tdfa_scan_ok(m) && parallel_findall_ok(m, p->prog) ? 1 : 0);
   kv("parallel_findall", parallel_findall_ok(m, p->prog) ? 1 : 0);
-  kv("tdfa_skip_len", m.t_skip_len);
-  kv("tdfa_skip_state", m.t_skip_state);
-  kv("tdfa_prefix_events", m.t_pre_n);
+  kv("scan6_image_bytes", (long long)m.w6_words * 4);
+  kv("scan6_descriptors", m.w6_ndesc);
+  kv("scan6_filter_distance", m.w6_d);
+  kv("scan6_p", m.w6_p);
+  kv("scan6_q", m.w6_q);
+  kv("w6_off", m.w6_off); kv("w6_desc", m.w6_desc); kv("w6_adesc", m.w6_adesc); kv("w6_aoff", m.w6_aoff);
+  kv("w6_alist", m.w6_alist); kv("w6_init", m.w6_init);
+  kv("tdfa_states", m.t_ns); kv("tdfa_tags", m.t_ntags); kv("tdfa_start_any", m.t_start_any); kv("tdfa_n_init_any", m.t_n_init_any);
   kv("run_anchor", m.run_ok);
   kv("run_literal", m.run_ok ? m.run_lit : -1);
   kv("run_linear_elements", m.lin_n);
@@ -432,6 +437,16 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   s += "\"}";
   if (buf && cap > s.size()) std::memcpy(buf, s.c_str(), s.size() + 1);
   return (int64_t)s.size();
+}
+
+// The packed device image itself (u32 words), for host-side tests of the packing: returns the number of words.
+int64_t rgx_program_device_image(const rgx_program* p, uint32_t* words_out, size_t cap_words) {
+  if (!p) { set_error("null argument"); return RGX_EINVAL; }
+  std::vector<uint32_t> words;
+  DevMeta m;
+  pack_program(p->prog, words, m);
+  if (words_out && cap_words >= words.size()) std::memcpy(words_out, words.data(), words.size() * 4);
+  return (int64_t)words.size();
 }
 
 }  // extern "C"

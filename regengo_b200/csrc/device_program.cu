@@ -226,6 +226,73 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       }
       align4();
     }
+    // scan6 walk image (layout: device_program.cuh).  The walk distinguishes only two kinds of step: CHEAP ones,
+    // whose whole effect is "go to that row", and EVENTS, which it logs and interprets when the walk is over.
+    if (m.prefix_len >= 1 && !nullable && t.start_begin == t.start_any && t.init_tags_begin == t.init_tags_any &&
+        lists.size() <= 1023 && t.num_tags <= 16) {
+      std::vector<uint32_t> rows((size_t)t.num_states * 256, S6_EVBIT);   // descriptor 0: dead
+      std::map<std::pair<int, uint32_t>, uint32_t> desc_ids;
+      std::vector<uint32_t> desc{0xFFFFFFFFu, 0u};
+      for (int st = 0; st < t.num_states; st++) {
+        const bool acc_s = t.accept[st] || t.accept_eot[st];
+        for (int c = 0; c < 128; c++) {
+          const size_t i = (size_t)st * 128 + c;
+          if (t.trans[i] < 0) continue;
+          const int nx = t.trans[i];
+          const uint32_t tl = list_id(t.actions[i]);
+          const bool acc_n = t.accept[nx] || t.accept_eot[nx];
+          if (tl == 0 && (nx == st || (!acc_s && !acc_n))) { rows[(size_t)st * 256 + c] = (uint32_t)nx * 1024u; continue; }
+          auto key = std::make_pair(nx, tl);
+          auto it = desc_ids.find(key);
+          uint32_t id;
+          if (it != desc_ids.end()) id = it->second;
+          else {
+            id = (uint32_t)(desc.size() / 2);
+            desc_ids[key] = id;
+            desc.push_back((uint32_t)nx * 1024u);
+            desc.push_back(tl | (list_id(t.accept_actions[nx]) << 10) | (t.accept[nx] ? S6_ACC : 0u) | (t.accept_eot[nx] ? S6_ACC_EOT : 0u));
+          }
+          rows[(size_t)st * 256 + c] = S6_EVBIT | id;
+        }
+      }
+      const size_t ndesc = desc.size() / 2;
+      const size_t bytes = (rows.size() + desc.size() + 3 * lists.size() + 64) * 4;
+      if (ndesc <= 1023 && bytes <= S6_IMAGE_LIMIT && lists.size() == ids.size()) {
+        align4();
+        m.w6_off = (uint32_t)w.size();
+        w.insert(w.end(), rows.begin(), rows.end());
+        m.w6_desc = (uint32_t)w.size() - m.w6_off;
+        w.insert(w.end(), desc.begin(), desc.end());
+        m.w6_ndesc = (int32_t)ndesc;
+        m.w6_adesc = (uint32_t)w.size() - m.w6_off;
+        for (auto& l : lists) {
+          bool simple = l.size() <= 3;
+          for (uint32_t x : l) if ((x >> 16) > 255 || (x & 0xFFFFu) > 255) simple = false;
+          uint32_t a[3] = {0, 0, 0};
+          if (simple) for (size_t i = 0; i < l.size(); i++) a[i] = (l[i] & 0xFFu) | (((l[i] >> 16) & 0xFFu) << 8);
+          w.push_back(a[0] | (a[1] << 16));
+          w.push_back(a[2] | ((simple ? (uint32_t)l.size() : 0u) << 16) | ((simple ? 0u : 1u) << 24));
+        }
+        m.w6_aoff = (uint32_t)w.size() - m.w6_off;
+        {
+          uint32_t pos = 0;
+          for (auto& l : lists) { w.push_back(pos); pos += (uint32_t)l.size(); }
+          w.push_back(pos);
+        }
+        m.w6_alist = (uint32_t)w.size() - m.w6_off;
+        for (auto& l : lists) w.insert(w.end(), l.begin(), l.end());
+        m.w6_init = (uint32_t)w.size() - m.w6_off;
+        for (int x : t.init_tags_any) w.push_back((uint32_t)x);
+        align4();
+        m.w6_words = (uint32_t)w.size() - m.w6_off;
+        m.w6_ok = 1;
+        // filter bytes: the first prefix byte and the last of the first four (both necessary for any match)
+        const int pl = m.prefix_len < 4 ? m.prefix_len : 4;
+        m.w6_p = m.prefix_bytes[0];
+        m.w6_d = pl - 1;
+        m.w6_q = m.prefix_bytes[pl - 1];
+      }
+    }
   } else {
     first_bytes_bt(P, first, nullable);
     int pc = prog.start;

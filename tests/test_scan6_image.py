@@ -1,0 +1,175 @@
+"""The scan6 walk image (csrc/device_program.cu) against the reference's TDFA walk (no GPU).
+
+The FindAll scan kernel does not run the reference's loop literally: it takes CHEAP steps (row lookups), logs
+EVENTS, and reads match end and tags off the log afterwards (kernels_scan6.cuh, "Exactness of reading the match off
+the log").  This test executes that procedure over the image the library actually packs -- rows, descriptors and
+tag lists are read from rgx_program_device_image -- and compares, for every start position of every corpus input
+of every TDFA pattern on the fast path, with a literal restatement of tdfa.go:929-983 over the TDFA tables of
+rgx_program_json.  What it pins is the packing and the claim that the log determines the reference's result; the
+kernel's own arithmetic is covered by the GPU parity tests."""
+import json
+import os
+
+import numpy as np
+
+import regengo_b200 as rg
+from regengo_b200 import synth
+
+from helpers import ROOT, compile_json
+
+EVBIT, ACC, ACC_EOT = 0x80000000, 1 << 20, 1 << 21
+
+
+def reference_walk(t, data, start):
+    """One start position of findBytesInternal (tdfa.go:929-983) -> (match_end, matchTags) or None."""
+    ns, nt = t["num_states"], t["num_tags"]
+    tags = [-1] * nt
+    tags[0] = start
+    state = t["start_begin"] if start == 0 else t["start_any"]
+    for tg in (t["init_tags_begin"] if start == 0 else t["init_tags_any"]):
+        tags[tg] = start
+    match_end, match_tags = -1, None
+    if t["accept"][state] or (start == len(data) and t["accept_eot"][state]):
+        match_end, match_tags = start, list(tags)
+    for i in range(start, len(data)):
+        c = data[i]
+        if c >= 128:
+            break
+        nx = t["trans"][state * 128 + c]
+        if nx < 0:
+            break
+        for tg, off in t["actions"].get(str(state * 128 + c), []):
+            tags[tg] = i + 1 - off
+        state = nx
+        if t["accept"][state] or (i == len(data) - 1 and t["accept_eot"][state]):
+            for tg, off in t["accept_actions"][state]:
+                tags[tg] = i + 1 - off
+            match_end, match_tags = i + 1, list(tags)
+    if match_end < 0:
+        return None
+    match_tags[1] = match_end
+    return match_end, match_tags
+
+
+class Image:
+    def __init__(self, pattern, **kw):
+        p = rg.Pattern(pattern, **kw)
+        self.plan = p.device_plan()
+        w = p.device_image()
+        d = self.plan
+        self.w = w[d["w6_off"]: d["w6_off"] + d["scan6_image_bytes"] // 4]
+        self.nt = d["tdfa_tags"]
+
+    def lists(self, li):
+        d = self.plan
+        lo, hi = int(self.w[d["w6_aoff"] + li]), int(self.w[d["w6_aoff"] + li + 1])
+        generic = [(int(x) & 0xFFFF, int(x) >> 16) for x in self.w[d["w6_alist"] + lo: d["w6_alist"] + hi]]
+        # the flattened descriptor must say the same
+        a, b = int(self.w[d["w6_adesc"] + 2 * li]), int(self.w[d["w6_adesc"] + 2 * li + 1])
+        if not (b >> 24):
+            n = (b >> 16) & 0xFF
+            flat = [(a & 0xFF, (a >> 8) & 0xFF), ((a >> 16) & 0xFF, a >> 24), (b & 0xFF, (b >> 8) & 0xFF)][:n]
+            assert flat == generic
+        return generic
+
+    def walk(self, data, start):
+        """The kernel's procedure: cheap steps, event log, interpretation of the log."""
+        d = self.plan
+        w = self.w
+        row = d["tdfa_start_any"] * 1024
+        ri, log, lastacc, eob = start, [], 0, False
+        while True:
+            if ri >= len(data):
+                eob = True
+                break
+            cell = int(w[row // 4 + data[ri]])
+            if not cell & EVBIT:
+                row = cell
+                ri += 1
+                continue
+            idx = cell & 0xFFFF
+            if idx == 0:
+                break
+            dx, dy = int(w[d["w6_desc"] + 2 * idx]), int(w[d["w6_desc"] + 2 * idx + 1])
+            log.append((idx, ri - start))
+            if dy & ACC:
+                lastacc = len(log)
+            row = dx
+            ri += 1
+        end_rel = ri - start
+        if eob and log:
+            dy = int(w[d["w6_desc"] + 2 * log[-1][0] + 1])
+            if dy & ACC_EOT:
+                lastacc = len(log)
+        if not lastacc:
+            return None, len(log)
+        match_end = log[lastacc][1] if lastacc < len(log) else end_rel
+        tags = [-1] * self.nt
+        tags[0] = 0
+        for j in range(d["tdfa_n_init_any"]):
+            tags[int(w[d["w6_init"] + j])] = 0
+        for e in range(lastacc):
+            idx, pos = log[e]
+            dy = int(w[d["w6_desc"] + 2 * idx + 1])
+            tl, al = dy & 0x3FF, (dy >> 10) & 0x3FF
+            if tl:
+                for tg, off in self.lists(tl):
+                    tags[tg] = pos + 1 - off
+            if al and ((dy & ACC) or e + 1 == lastacc):
+                run_end = log[e + 1][1] if e + 1 < len(log) else end_rel
+                for tg, off in self.lists(al):
+                    tags[tg] = run_end - off
+        tags[1] = match_end
+        return (match_end, tags), len(log)
+
+
+def check_pattern(pattern, inputs, **kw):
+    img = Image(pattern, **kw)
+    if not img.plan["fast_tdfa_scan"]:
+        return 0
+    t = compile_json(pattern, **kw)["tdfa"]
+    assert t["start_begin"] == t["start_any"]
+    n = 0
+    for data in inputs:
+        for start in range(len(data)):
+            # the filter's condition is necessary: a start it rejects cannot match
+            pd = img.plan["scan6_filter_distance"]
+            passes = data[start] == img.plan["scan6_p"] and (pd == 0 or (start + pd < len(data) and data[start + pd] == img.plan["scan6_q"]))
+            ref = reference_walk(t, data, start)
+            if not passes:
+                assert ref is None, (pattern, data, start)
+                continue
+            got, nlog = img.walk(data, start)
+            if ref is None:
+                assert got is None, (pattern, data, start)
+            else:
+                assert got is not None, (pattern, data, start)
+                rel = [x - start if x >= 0 else -1 for x in ref[1]]
+                assert (got[0], got[1]) == (ref[0] - start, rel), (pattern, data, start, got, ref)
+            n += 1
+    return n
+
+
+def test_url_pattern_log_interpretation():
+    pool, nw, nu = synth._url_pool()
+    urls = [bytes(pool.mat[i, :pool.lens[i]]) for i in range(nw, nw + 300)]
+    inputs = [b"see " + u + b"and " + u for u in urls[:150]] + [u.rstrip() for u in urls[150:]]   # also URLs cut by the end of the input
+    inputs += [b"http://a.b:80/x", b"https://", b"http://a", b"http://a.b:/x", b"http://a.b:8", b"http://\xc3\xa9.com", b"httphttp://x.y/http://z"]
+    assert check_pattern(synth.URL_PATTERN, inputs) > 400
+
+
+def test_corpus_tdfa_patterns_log_interpretation():
+    corpus = json.load(open(os.path.join(ROOT, "tests", "golden", "corpus_expected.json")))
+    n_pat = 0
+    for ent in corpus["e2e"] + corpus["curated"]:
+        if ent["n_groups"] == 0:
+            continue
+        for kw in ({}, {"force_tdfa": True}):
+            try:
+                inputs = [c["input"].encode("utf-8") for c in ent["cases"]]
+                inputs.append(b" ".join(inputs))
+                if check_pattern(ent["pattern"], inputs, **kw):
+                    n_pat += 1
+            except rg.RegengoError:
+                pass
+    assert n_pat >= 15
