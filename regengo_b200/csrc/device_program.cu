@@ -165,19 +165,6 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     for (int x : t.init_tags_begin) w.push_back((uint32_t)x);
     for (int x : t.init_tags_any) w.push_back((uint32_t)x);
     align4();
-    // fast cells: everything one walk step needs in a single shared-memory word
-    if (t.num_states < (int)FAST_NONE && lists.size() <= 1023) {
-      m.off_t_fast = (uint32_t)w.size();
-      for (size_t i = 0; i < (size_t)t.num_states * 128; i++) {
-        if (t.trans[i] < 0) { w.push_back(FAST_NONE); continue; }
-        const int nx = t.trans[i];
-        uint32_t cell = (uint32_t)nx | (list_id(t.actions[i]) << 10) | (list_id(t.accept_actions[nx]) << 20);
-        if (t.accept[nx]) cell |= 1u << 30;
-        if (t.accept_eot[nx]) cell |= 1u << 31;
-        w.push_back(cell);
-      }
-      align4();
-    }
     // start filter from the tables: bytes with a transition out of startStateAny
     nullable = t.accept[t.start_any] || t.accept_eot[t.start_any];
     for (uint32_t c = 0; c < 128; c++) if (t.trans[(size_t)t.start_any * 128 + c] >= 0) first.set(c);
@@ -193,46 +180,15 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       s = t.trans[(size_t)s * 128 + only];
       prefix_states.push_back(s);
     }
-    if (m.off_t_fast) {
-      // walks may skip the verified prefix up to the last state that does not accept
-      int skip = m.prefix_len < 4 ? m.prefix_len : 4;   // the filter compares at most 4 prefix bytes
-      while (skip > 0 && (t.accept[prefix_states[skip]] || t.accept_eot[prefix_states[skip]])) skip--;
-      m.t_skip_len = skip;
-      m.t_skip_state = prefix_states[skip];
-      for (int i = 0; i < skip; i++)
-        if (prefix_lists[i]) m.t_pre_ev[m.t_pre_n++] = (prefix_lists[i] << 22) | (uint32_t)(i + 1);
-      // per state: the "boring" cell (same state, no transition list), identical for every byte that has it
-      m.off_t_selftab = (uint32_t)w.size();
-      for (int st = 0; st < t.num_states; st++) {
-        uint32_t self = 0xFFFFFFFFu;
-        for (int c = 0; c < 128; c++) {
-          const uint32_t cell = w[m.off_t_fast + (size_t)st * 128 + c];
-          if ((cell & 0x3FFu) == (uint32_t)st && ((cell >> 10) & 0x3FFu) == 0) self = cell;
-        }
-        w.push_back(self);
-      }
-      align4();
-      // action lists flattened for the replay, 2 words per list: word0 = a0 | a1 << 16, word1 = a2 | n << 16 |
-      // generic << 24 with a = tag:8 | offset:8.  Lists with more than 3 actions or fields above 255 set
-      // `generic` and are replayed from the list arrays.
-      m.off_t_adesc = (uint32_t)w.size();
-      for (auto& l : lists) {
-        bool simple = l.size() <= 3;
-        for (uint32_t x : l) if ((x >> 16) > 255 || (x & 0xFFFFu) > 255) simple = false;
-        uint32_t a[3] = {0, 0, 0};
-        if (simple) for (size_t i = 0; i < l.size(); i++) a[i] = (l[i] & 0xFFu) | (((l[i] >> 16) & 0xFFu) << 8);
-        w.push_back(a[0] | (a[1] << 16));
-        w.push_back(a[2] | ((simple ? (uint32_t)l.size() : 0u) << 16) | ((simple ? 0u : 1u) << 24));
-      }
-      align4();
-    }
     // scan6 walk image (layout: device_program.cuh).  The walk distinguishes only two kinds of step: CHEAP ones,
     // whose whole effect is "go to that row", and EVENTS, which it logs and interprets when the walk is over.
     if (m.prefix_len >= 1 && !nullable && t.start_begin == t.start_any && t.init_tags_begin == t.init_tags_any &&
         lists.size() <= 1023 && t.num_tags <= 16) {
-      std::vector<uint32_t> rows((size_t)t.num_states * 256, S6_EVBIT);   // descriptor 0: dead
+      std::vector<uint32_t> rows((size_t)t.num_states * 256, S6_DEAD);
       std::map<std::pair<int, uint32_t>, uint32_t> desc_ids;
-      std::vector<uint32_t> desc{0xFFFFFFFFu, 0u};
+      std::vector<uint32_t> desc{0u};                 // descriptor 0: "no event" (cheap cells carry index 0)
+      std::vector<uint32_t> fent{0u, 0u, 0u, 0u};     // S6_FENT entry words per descriptor
+      bool fits = true;
       for (int st = 0; st < t.num_states; st++) {
         const bool acc_s = t.accept[st] || t.accept_eot[st];
         for (int c = 0; c < 128; c++) {
@@ -247,50 +203,44 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
           uint32_t id;
           if (it != desc_ids.end()) id = it->second;
           else {
-            id = (uint32_t)(desc.size() / 2);
+            id = (uint32_t)desc.size();
             desc_ids[key] = id;
-            desc.push_back((uint32_t)nx * 1024u);
-            desc.push_back(tl | (list_id(t.accept_actions[nx]) << 10) | (t.accept[nx] ? S6_ACC : 0u) | (t.accept_eot[nx] ? S6_ACC_EOT : 0u));
+            // the event's effect on the tags, in the order the reference applies it: the transition's actions at the
+            // step's position, then (while the next state accepts) that state's accept actions at the end of its run
+            std::vector<uint32_t> ent;
+            for (const TagAction& x : t.actions[i]) {
+              if (x.tag >= 16 || x.offset > 255 || x.offset < 0) fits = false;
+              ent.push_back((uint32_t)x.tag * 128u | ((uint32_t)x.offset << 16));
+            }
+            if (acc_n)
+              for (const TagAction& x : t.accept_actions[nx]) {
+                if (x.tag >= 16 || x.offset > 255 || x.offset < 0) fits = false;
+                ent.push_back((uint32_t)x.tag * 128u | ((uint32_t)x.offset << 16) | S6_ENT_ACCEPT);
+              }
+            if (ent.size() > S6_FENT) fits = false;
+            desc.push_back((t.accept[nx] ? S6_ACC : 0u) | (t.accept_eot[nx] ? S6_ACC_EOT : 0u) | ((uint32_t)std::min<size_t>(ent.size(), S6_FENT) << 24));
+            ent.resize(S6_FENT, 0u);
+            fent.insert(fent.end(), ent.begin(), ent.end());
           }
-          rows[(size_t)st * 256 + c] = S6_EVBIT | id;
+          rows[(size_t)st * 256 + c] = (id << 22) | ((uint32_t)nx * 1024u);
         }
       }
-      const size_t ndesc = desc.size() / 2;
-      const size_t bytes = (rows.size() + desc.size() + 3 * lists.size() + 64) * 4;
-      if (ndesc <= 1023 && bytes <= S6_IMAGE_LIMIT && lists.size() == ids.size()) {
+      const size_t ndesc = desc.size();
+      const size_t bytes = (rows.size() + desc.size() + fent.size() + 64) * 4;
+      if (fits && ndesc <= 1022 && (size_t)t.num_states * 1024 < (1u << 22) && bytes <= S6_IMAGE_LIMIT) {
         align4();
         m.w6_off = (uint32_t)w.size();
         w.insert(w.end(), rows.begin(), rows.end());
         m.w6_desc = (uint32_t)w.size() - m.w6_off;
         w.insert(w.end(), desc.begin(), desc.end());
         m.w6_ndesc = (int32_t)ndesc;
-        m.w6_adesc = (uint32_t)w.size() - m.w6_off;
-        for (auto& l : lists) {
-          bool simple = l.size() <= 3;
-          for (uint32_t x : l) if ((x >> 16) > 255 || (x & 0xFFFFu) > 255) simple = false;
-          uint32_t a[3] = {0, 0, 0};
-          if (simple) for (size_t i = 0; i < l.size(); i++) a[i] = (l[i] & 0xFFu) | (((l[i] >> 16) & 0xFFu) << 8);
-          w.push_back(a[0] | (a[1] << 16));
-          w.push_back(a[2] | ((simple ? (uint32_t)l.size() : 0u) << 16) | ((simple ? 0u : 1u) << 24));
-        }
-        m.w6_aoff = (uint32_t)w.size() - m.w6_off;
-        {
-          uint32_t pos = 0;
-          for (auto& l : lists) { w.push_back(pos); pos += (uint32_t)l.size(); }
-          w.push_back(pos);
-        }
-        m.w6_alist = (uint32_t)w.size() - m.w6_off;
-        for (auto& l : lists) w.insert(w.end(), l.begin(), l.end());
+        m.w6_fent = (uint32_t)w.size() - m.w6_off;
+        w.insert(w.end(), fent.begin(), fent.end());
         m.w6_init = (uint32_t)w.size() - m.w6_off;
         for (int x : t.init_tags_any) w.push_back((uint32_t)x);
         align4();
         m.w6_words = (uint32_t)w.size() - m.w6_off;
         m.w6_ok = 1;
-        // filter bytes: the first prefix byte and the last of the first four (both necessary for any match)
-        const int pl = m.prefix_len < 4 ? m.prefix_len : 4;
-        m.w6_p = m.prefix_bytes[0];
-        m.w6_d = pl - 1;
-        m.w6_q = m.prefix_bytes[pl - 1];
       }
     }
   } else {

@@ -21,9 +21,11 @@ namespace rgx {
 constexpr int MAX_CAPS = 32;         // 2*(k+1) <= 32 on the device paths
 constexpr int MAX_PREFIX = 8;
 constexpr uint32_t TDFA_NONE = 0xFFFFu;
-constexpr uint32_t FAST_NONE = 0x3FFu;   // next-state field of a fast cell with no transition
-constexpr uint32_t S6_EVBIT = 0x80000000u;   // scan6 cell: not a cheap step, low bits = event descriptor index
-constexpr uint32_t S6_ACC = 1u << 20, S6_ACC_EOT = 1u << 21;   // scan6 descriptor word 1 flags
+constexpr uint32_t S6_DEAD = 0xFFC00000u;    // scan6 cell without a transition (every cell >= S6_DEAD is dead)
+constexpr uint32_t S6_EVMIN = 0x00400000u;   // scan6 cells >= S6_EVMIN (and < S6_DEAD) are events
+constexpr uint32_t S6_ACC = 1u << 20, S6_ACC_EOT = 1u << 21;   // scan6 descriptor flags
+constexpr uint32_t S6_FENT = 4;                  // tag entries per scan6 descriptor
+constexpr uint32_t S6_ENT_ACCEPT = 0x80000000u;  // scan6 tag entry: an accept action of the event's next state
 constexpr uint32_t S6_IMAGE_LIMIT = 96 * 1024;   // bytes of walk image staged per CTA
 constexpr uint32_t SMEM_IMAGE_LIMIT = 160 * 1024;
 
@@ -35,31 +37,22 @@ struct DevMeta {
   uint32_t image_words;        // multiple of 4
   uint32_t off_inst, off_cls, off_th_eps, off_th_cond, off_rng_idx, off_rng_pairs;
   uint32_t off_t_trans, off_t_accept, off_t_alist_off, off_t_alist, off_t_init, off_first;
-  // "fast" TDFA cells (0 = absent): next:10 | transition alist:10 | accept alist of NEXT:10 | next accepts:1 | next accepts at EOT:1
-  uint32_t off_t_fast;
-  // scan5 extras (0 = absent): per state, the cell that stays in the state without tag actions (or ~0u);
-  // per action list, a 64-bit descriptor {n:8 | (tag:8, offset:8) x 3} chained by list id (see pack_program)
-  uint32_t off_t_selftab, off_t_adesc;
-  // walks of verified candidates start after `t_skip_len` prefix bytes, in state `t_skip_state`, with
-  // `t_pre_n` tag events already logged (every state on the way is non-accepting)
-  int32_t t_skip_len, t_skip_state, t_pre_n;
-  uint32_t t_pre_ev[8];
   // scan6 walk image (kernels_scan6.cuh; w6_ok = 0: absent): the contiguous sub-range [w6_off, w6_off + w6_words) of the
   // image is all the FindAll scan stages into shared memory.  Offsets below are in words, relative to w6_off:
-  //   rows   t_ns x 256 cells at 0.  A CHEAP cell (bit 31 clear) is the byte offset of the next state's row: no
+  //   rows   t_ns x 256 cells at 0: idx:10 << 22 | byte offset of the next state's row.  idx 0 = CHEAP step: no
   //          transition tag list fires and the step is either a self-loop or a move between two states that accept
-  //          neither in the text nor at its end.  Every other cell is S6_EVBIT | descriptor index; index 0 = dead
-  //          (no transition; bytes >= 128 included, tdfa.go:944-946).
-  //   desc   2 words per descriptor: {byte offset of the next row, tl:10 | al:10 | accepts:1 | accepts at EOT:1}
-  //          (tl = transition tag list, al = accept tag list of the next state)
-  //   adesc / aoff / alist   the de-duplicated tag lists (same encoding as off_t_adesc / off_t_alist_off / off_t_alist)
+  //          neither in the text nor at its end.  idx 0x3FF (S6_DEAD) = no transition (bytes >= 128 included,
+  //          tdfa.go:944-946).  Any other idx = EVENT, described by desc[idx].
+  //   desc   1 word per descriptor: accepts:1 (S6_ACC) | accepts at EOT:1 (S6_ACC_EOT) | n:3 << 24 -- flags of the event's
+  //          next state and the number of tag entries
+  //   fent   S6_FENT words per descriptor, the event's tag actions in application order: tag * 128 | offset:8 << 16,
+  //          S6_ENT_ACCEPT set on the next state's accept actions (applied at the end of the state's run, and only
+  //          while that state accepts); the others are the transition's actions (applied at the step's position)
   //   init   tags set to the start position by initialTagsAny
-  uint32_t w6_off, w6_words, w6_desc, w6_adesc, w6_aoff, w6_alist, w6_init;
+  uint32_t w6_off, w6_words, w6_desc, w6_fent, w6_init;
   int32_t w6_ok, w6_ndesc;
-  // start filter of scan6: byte w6_p at the candidate start and (w6_d > 0) byte w6_q at start + w6_d, both taken
-  // from the literal prefix; necessary, not sufficient -- the walk starts in startStateAny at the candidate start
-  int32_t w6_d;
-  uint8_t w6_p, w6_q, w6_pad[2];
+  // (start filter of scan6: up to three of the first four bytes of the literal prefix -- necessary, not sufficient;
+  // the walk starts in startStateAny at the candidate start)
   int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
   uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;
   // FindAll candidate generator (start filter); see findall_kernels.cu

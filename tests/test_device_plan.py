@@ -12,8 +12,8 @@ from helpers import ROOT
 def test_bench_patterns_take_the_fast_paths():
     url = rg.Pattern(synth.URL_PATTERN).device_plan()
     assert url["find_engine"] == 2 and url["fast_tdfa_scan"] == 1 and url["parallel_findall"] == 1
-    # the filter tests 'h' and, three bytes on, 'p'; 13 rows of 256 cells + 7 event descriptors + the dead one
-    assert bytes.fromhex(url["prefix"]) == b"http" and url["scan6_filter_distance"] == 3 and url["scan6_descriptors"] == 8
+    # 13 rows of 256 cells, 7 event descriptors + the empty one
+    assert bytes.fromhex(url["prefix"]) == b"http" and url["scan6_descriptors"] == 8
     assert 13 * 1024 <= url["scan6_image_bytes"] <= 16 * 1024
     email = rg.Pattern(synth.EMAIL_PATTERN).device_plan()
     assert email["find_engine"] == 1 and email["run_anchor"] == 1 and email["run_literal"] == ord("@")
@@ -51,7 +51,7 @@ def test_plan_invariants_over_the_corpus():
         d = p.device_plan()
         n += 1
         if d["fast_tdfa_scan"]:
-            assert d["find_engine"] == 2 and d["prefix_len"] >= 1 and d["nullable"] == 0 and d["scan6_filter_distance"] == min(4, d["prefix_len"]) - 1
+            assert d["find_engine"] == 2 and d["prefix_len"] >= 1 and d["nullable"] == 0
             assert 0 < d["scan6_image_bytes"] <= 96 * 1024 and 1 <= d["scan6_descriptors"] <= 1023
         if d["run_linear_elements"]:
             assert d["run_anchor"] == 1 and d["find_engine"] == 1

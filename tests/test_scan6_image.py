@@ -17,7 +17,7 @@ from regengo_b200 import synth
 
 from helpers import ROOT, compile_json
 
-EVBIT, ACC, ACC_EOT = 0x80000000, 1 << 20, 1 << 21
+DEAD, EVMIN, ACC, ACC_EOT = 0xFFC00000, 0x00400000, 1 << 20, 1 << 21
 
 
 def reference_walk(t, data, start):
@@ -60,17 +60,16 @@ class Image:
         self.w = w[d["w6_off"]: d["w6_off"] + d["scan6_image_bytes"] // 4]
         self.nt = d["tdfa_tags"]
 
-    def lists(self, li):
+    def entries(self, idx):
+        """Tag entries of descriptor idx: [(tag, offset, is_accept_action)]."""
         d = self.plan
-        lo, hi = int(self.w[d["w6_aoff"] + li]), int(self.w[d["w6_aoff"] + li + 1])
-        generic = [(int(x) & 0xFFFF, int(x) >> 16) for x in self.w[d["w6_alist"] + lo: d["w6_alist"] + hi]]
-        # the flattened descriptor must say the same
-        a, b = int(self.w[d["w6_adesc"] + 2 * li]), int(self.w[d["w6_adesc"] + 2 * li + 1])
-        if not (b >> 24):
-            n = (b >> 16) & 0xFF
-            flat = [(a & 0xFF, (a >> 8) & 0xFF), ((a >> 16) & 0xFF, a >> 24), (b & 0xFF, (b >> 8) & 0xFF)][:n]
-            assert flat == generic
-        return generic
+        n = int(self.w[d["w6_desc"] + idx]) >> 24
+        out = []
+        for i in range(n):
+            en = int(self.w[d["w6_fent"] + 4 * idx + i])
+            assert (en & 0xFFFF) % 128 == 0
+            out.append(((en & 0xFFFF) // 128, (en >> 16) & 0xFF, bool(en >> 31)))
+        return out
 
     def walk(self, data, start):
         """The kernel's procedure: cheap steps, event log, interpretation of the log."""
@@ -83,24 +82,18 @@ class Image:
                 eob = True
                 break
             cell = int(w[row // 4 + data[ri]])
-            if not cell & EVBIT:
-                row = cell
-                ri += 1
-                continue
-            idx = cell & 0xFFFF
-            if idx == 0:
+            if cell >= DEAD:
                 break
-            dx, dy = int(w[d["w6_desc"] + 2 * idx]), int(w[d["w6_desc"] + 2 * idx + 1])
-            log.append((idx, ri - start))
-            if dy & ACC:
-                lastacc = len(log)
-            row = dx
+            if cell >= EVMIN:
+                log.append((cell >> 22, ri - start))
+            row = cell & 0x3FFFFF
             ri += 1
+        # the last event whose next state accepts
+        for e, (idx, _) in enumerate(log):
+            dy = int(w[d["w6_desc"] + idx])
+            if dy & ACC or (e + 1 == len(log) and eob and dy & ACC_EOT):
+                lastacc = e + 1
         end_rel = ri - start
-        if eob and log:
-            dy = int(w[d["w6_desc"] + 2 * log[-1][0] + 1])
-            if dy & ACC_EOT:
-                lastacc = len(log)
         if not lastacc:
             return None, len(log)
         match_end = log[lastacc][1] if lastacc < len(log) else end_rel
@@ -110,14 +103,13 @@ class Image:
             tags[int(w[d["w6_init"] + j])] = 0
         for e in range(lastacc):
             idx, pos = log[e]
-            dy = int(w[d["w6_desc"] + 2 * idx + 1])
-            tl, al = dy & 0x3FF, (dy >> 10) & 0x3FF
-            if tl:
-                for tg, off in self.lists(tl):
+            dy = int(w[d["w6_desc"] + idx])
+            run_end = log[e + 1][1] if e + 1 < len(log) else end_rel
+            accp = bool(dy & ACC) or e + 1 == lastacc
+            for tg, off, is_acc in self.entries(idx):
+                if not is_acc:
                     tags[tg] = pos + 1 - off
-            if al and ((dy & ACC) or e + 1 == lastacc):
-                run_end = log[e + 1][1] if e + 1 < len(log) else end_rel
-                for tg, off in self.lists(al):
+                elif accp:
                     tags[tg] = run_end - off
         tags[1] = match_end
         return (match_end, tags), len(log)
@@ -133,8 +125,9 @@ def check_pattern(pattern, inputs, **kw):
     for data in inputs:
         for start in range(len(data)):
             # the filter's condition is necessary: a start it rejects cannot match
-            pd = img.plan["scan6_filter_distance"]
-            passes = data[start] == img.plan["scan6_p"] and (pd == 0 or (start + pd < len(data) and data[start + pd] == img.plan["scan6_q"]))
+            pre = bytes.fromhex(img.plan["prefix"])[:4]
+            tested = [0, 1, 3] if len(pre) == 4 else list(range(len(pre)))   # the prefix bytes the filter compares
+            passes = all(start + o < len(data) and data[start + o] == pre[o] for o in tested)
             ref = reference_walk(t, data, start)
             if not passes:
                 assert ref is None, (pattern, data, start)

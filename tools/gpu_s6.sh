@@ -1,21 +1,26 @@
 #!/bin/bash
-# scan6 iteration pass: FindAll parity tests, c3 bench at several span sizes, one full ncu capture of the scan.
+# scan6 iteration pass: FindAll parity tests, c3 bench at several tunings, one full ncu capture of the scan.
 tag=${1:-s6}
 out=gpurun_out/$tag
 mkdir -p $out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "find_all or fast_scan or forced" > $out/pytest.log 2>&1; echo "pytest rc=$?" >> $out/pytest.log
 tail -5 $out/pytest.log
-for U in 1 2 4; do
-  RGX_SCAN_U=$U timeout 300 python bench.py --workload c3 --steps 10 --no-e2e --no-cpu > $out/bench_c3_U$U.json 2> $out/bench_c3_U$U.err
+run() {
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --workload c3 --steps 10 --no-e2e --no-cpu > $out/bench_c3_$name.json 2> $out/bench_c3_$name.err
   python - <<PY
 import json
 try:
-    d=json.load(open("$out/bench_c3_U$U.json"))
-    r=d["roofline"]; print("U=$U value %.0f GB/s  scan %.3f ms chain %.3f emit %.3f frac %.3f matches %d recs %d" % (d["value"], r["scan_ms"], r["chain_ms"], r["emit_ms"], r["frac"], d["config"]["matches_per_step"], d["config"]["distinct_records_per_step"]))
+    d=json.load(open("$out/bench_c3_$name.json"))
+    r=d["roofline"]; print("$name value %.0f GB/s  scan %.3f ms chain %.3f emit %.3f frac %.3f matches %d recs %d" % (d["value"], r["scan_ms"], r["chain_ms"], r["emit_ms"], r["frac"], d["config"]["matches_per_step"], d["config"]["distinct_records_per_step"]))
 except Exception as e:
-    print("U=$U failed", e); print(open("$out/bench_c3_U$U.err").read()[-2000:])
+    print("$name failed", e); print(open("$out/bench_c3_$name.err").read()[-2000:])
 PY
-done
+}
+run G2 RGX_SCAN_GROUPS=2
+run G3 RGX_SCAN_GROUPS=3
+run G3W12 RGX_SCAN_GROUPS=3 RGX_SCAN_CFG=1
+run G2W12 RGX_SCAN_GROUPS=2 RGX_SCAN_CFG=1
 if [ "$2" != "noncu" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:findall_scan6 -s 3 -c 1 -o $out/scan6_c3 \
    python bench.py --workload c3 --gib 1 --steps 1 --warmup 3 --no-e2e --no-cpu > $out/ncu_full_c3.log 2>&1
