@@ -87,8 +87,9 @@ class Oracle:
             raise RuntimeError("Find* is not generated for a pattern without captures")
         return out.tolist() if r == 1 else None
 
-    def find_all(self, data, n=-1, cap=None):
-        """FindAllBytes(data, n): (count, int64 array [min(count,cap), num_cap])."""
+    def find_all(self, data, n=-1, cap=None, count_only=False):
+        """FindAllBytes(data, n): (count, int64 array [min(count,cap), num_cap]).  count_only: one pass, the count and
+        whatever fitted `cap` (timing runs)."""
         a = _as_u8(data)
         L = _load()
         if cap is None:
@@ -97,6 +98,8 @@ class Oracle:
         cnt = L.orc_find_all(self._h, a.ctypes.data, a.size, n, out.ctypes.data, cap)
         if cnt < 0:
             raise RuntimeError("FindAll* is not generated for a pattern without captures")
+        if count_only:
+            return int(cnt), out[:min(cnt, cap)]
         if cnt > cap:
             return self.find_all(data, n, cap=int(cnt))
         return int(cnt), out[:cnt]
@@ -108,7 +111,7 @@ class Oracle:
             raise ValueError("stream: buffer size too small")
         return b.value, l.value
 
-    def find_reader(self, data, buffer_size=0, max_leftover=0, cap=None):
+    def find_reader(self, data, buffer_size=0, max_leftover=0, cap=None, count_only=False):
         """FindReader over bytes.Reader(data): (count, stream_off[], chunk_idx[], records[])."""
         a = _as_u8(data)
         L = _load()
@@ -121,6 +124,9 @@ class Oracle:
                                 out.ctypes.data, cap)
         if cnt == -6:
             raise ValueError("stream: buffer size too small")
+        if count_only:
+            k = min(cnt, cap)
+            return int(cnt), so[:k], ci[:k], out[:k]
         if cnt > cap:
             return self.find_reader(data, buffer_size, max_leftover, cap=int(cnt))
         return int(cnt), so[:cnt], ci[:cnt], out[:cnt]

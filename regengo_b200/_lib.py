@@ -46,6 +46,8 @@ _SIGS = {
     "rgx_ctx_sync": (C.c_int, [_P]),
     "rgx_match_batch": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
     "rgx_match_batch_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
+    "rgx_match_multi": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P]),
+    "rgx_match_multi_dev": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P]),
     "rgx_find_batch": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
     "rgx_find_batch_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
     "rgx_find_all": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, C.c_uint64]),

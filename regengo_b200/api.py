@@ -95,6 +95,22 @@ def pack_inputs(inputs):
     return data, offs
 
 
+def match_multi(patterns, data, offsets, prog_first, device=0):
+    """Batched MatchBytes of MANY patterns in one launch (rgx_match_multi): inputs prog_first[p] .. prog_first[p+1]-1 of
+    the packed batch (uint8 data, uint64 offsets[n+1]) are matched against patterns[p].  -> uint8[n]"""
+    data = _as_u8(data)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    pf = np.ascontiguousarray(prog_first, dtype=np.uint64)
+    assert pf.size == len(patterns) + 1
+    n = int(pf[-1] - pf[0])
+    out = np.zeros(n, dtype=np.uint8)
+    handles = (C.c_void_p * len(patterns))(*[p._h for p in patterns])
+    if n:
+        check(_lib.load().rgx_match_multi(context(device), handles, len(patterns), data.ctypes.data, offs.ctypes.data,
+                                          pf.ctypes.data, out.ctypes.data))
+    return out
+
+
 class Pattern:
     """A compiled pattern == one generated regengo type."""
 

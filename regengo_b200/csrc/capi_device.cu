@@ -43,6 +43,8 @@ struct rgx_ctx {
   int64_t launches = 0;
   // grow-only scratch
   DevBuf stack, cstack, visited, small, in_bytes, in_offs, out_flag, out_rec, out_reps, out_aux;
+  DevBuf mm_tab;                       // match_multi: metas | image pointers | item_base | prog_first
+  std::vector<uint8_t> mm_key;         // host copy of the last table uploaded (skips the upload when nothing changed)
   DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase, ch_segsel, ch_segreps, ch_entry, ch_tile;
   void* h_small = nullptr;  // pinned, 4 KiB
   uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
@@ -192,6 +194,104 @@ void release_device_program(rgx_program* p) {
 }
 }  // namespace rgx
 
+// ---- batched MatchBytes for many programs in ONE launch -------------------------------------------------
+template <typename OFFT>
+static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_progs, const uint8_t* d_bytes, const OFFT* d_offs,
+                           const uint64_t* prog_first, uint8_t* d_out) {
+  if (!c || !progs || !prog_first || n_progs == 0) { set_error("null argument"); return RGX_EINVAL; }
+  const uint64_t n = prog_first[n_progs];
+  for (uint32_t p = 0; p < n_progs; p++)
+    if (!progs[p] || prog_first[p] > prog_first[p + 1]) { set_error("rgx_match_multi: bad program table"); return RGX_EINVAL; }
+  if (n == prog_first[0]) return RGX_OK;
+  CU(cudaSetDevice(c->device));
+  // table: metas | image pointers | item_base | prog_first
+  std::vector<const DeviceImage*> ims(n_progs);
+  bool any_bt = false;
+  for (uint32_t p = 0; p < n_progs; p++) {
+    int rc = get_image(c, progs[p], &ims[p]);
+    if (rc) return rc;
+    if ((rc = check_caps(ims[p], false))) return rc;
+    any_bt = any_bt || ims[p]->meta.match_engine == MATCH_BT;
+  }
+  // items: runs of tiles of one program, sized so that a few CTAs per SM cover the batch
+  uint64_t total_tiles = 0;
+  for (uint32_t p = 0; p < n_progs; p++) total_tiles += (prog_first[p + 1] - prog_first[p] + MM_TILE - 1) / MM_TILE;
+  const uint64_t target_items = (uint64_t)c->sm_count * 16;
+  const uint32_t tiles_per_item = (uint32_t)std::max<uint64_t>(1, (total_tiles + target_items - 1) / target_items);
+  std::vector<uint32_t> item_base(n_progs + 1, 0);
+  for (uint32_t p = 0; p < n_progs; p++) {
+    const uint64_t tiles = (prog_first[p + 1] - prog_first[p] + MM_TILE - 1) / MM_TILE;
+    const uint64_t items = (tiles + tiles_per_item - 1) / tiles_per_item;
+    if (item_base[p] + items > 0x7FFFFFFFull) { set_error("rgx_match_multi: batch too large"); return RGX_EINVAL; }
+    item_base[p + 1] = item_base[p] + (uint32_t)items;
+  }
+  const size_t off_ptr = (size_t)n_progs * sizeof(DevMeta), off_item = off_ptr + (size_t)n_progs * 8,
+               off_first = (off_item + (size_t)(n_progs + 1) * 4 + 7) & ~(size_t)7, tab_bytes = off_first + (size_t)(n_progs + 1) * 8;
+  std::vector<uint8_t> tab(tab_bytes, 0);
+  for (uint32_t p = 0; p < n_progs; p++) {
+    std::memcpy(&tab[(size_t)p * sizeof(DevMeta)], &ims[p]->meta, sizeof(DevMeta));
+    const uint32_t* dp = ims[p]->d_words;
+    std::memcpy(&tab[off_ptr + (size_t)p * 8], &dp, 8);
+  }
+  std::memcpy(&tab[off_item], item_base.data(), (size_t)(n_progs + 1) * 4);
+  std::memcpy(&tab[off_first], prog_first, (size_t)(n_progs + 1) * 8);
+  int rc;
+  if (tab != c->mm_key || !c->mm_tab.p) {
+    if ((rc = ensure(c, c->mm_tab, tab_bytes))) return rc;
+    CU(cudaMemcpyAsync(c->mm_tab.p, tab.data(), tab_bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));   // (pageable source: the copy must be over before `tab` goes away)
+    c->mm_key = tab;
+  }
+  MultiArgs a;
+  a.metas = (const DevMeta*)c->mm_tab.p;
+  a.images = (const uint32_t* const*)((const char*)c->mm_tab.p + off_ptr);
+  a.item_base = (const uint32_t*)((const char*)c->mm_tab.p + off_item);
+  a.prog_first = (const unsigned long long*)((const char*)c->mm_tab.p + off_first);
+  a.n_progs = n_progs; a.n_items = item_base[n_progs]; a.tiles_per_item = tiles_per_item;
+
+  Small sm = small_of(c);
+  uint64_t max_len = 0;
+  if (any_bt) {   // sizes the per-thread backtracking scratch; Thompson-only batches need none
+    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
+    max_len_multi_kernel<OFFT><<<std::max(1, c->sm_count * 4), 256, 0, c->stream>>>(d_offs + prog_first[0], n - prog_first[0], sm.slots);
+    c->launches++;
+    if ((rc = read_small(c, 256))) return rc;
+    max_len = *(unsigned long long*)((char*)c->h_small + 64);
+  }
+  const size_t smem = MM_IMAGE_BYTES + MM_TILE_BYTES;
+  auto kern = match_multi_kernel<OFFT>;
+  int grid = 0;
+  if ((rc = occupancy_grid(c, kern, MM_TILE, smem, &grid))) return rc;
+  if ((uint32_t)grid > a.n_items) grid = (int)a.n_items;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    // one scratch plan for the whole launch: the largest need over the programs
+    ScratchPlan sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.stride = (uint32_t)grid * MM_TILE;
+    const uint32_t cap = attempt == 0 ? (uint32_t)std::min<uint64_t>(2 * max_len + 64, 1u << 20) : 0;
+    for (uint32_t p = 0; p < n_progs; p++) {
+      ScratchPlan one;
+      rc = plan_scratch(c, ims[p]->meta, false, sp.stride, max_len, cap, true, &one);
+      if (rc) break;
+      sp.stack_cap = std::max(sp.stack_cap, one.stack_cap); sp.visited_words = std::max(sp.visited_words, one.visited_words);
+    }
+    if (rc == RGX_ENOMEM && grid > c->sm_count) { grid = c->sm_count; attempt--; continue; }
+    if (rc) return rc;
+    // (plan_scratch grows the buffers monotonically, so after the loop they hold the largest request)
+    sp.stack = (uint2*)c->stack.p; sp.visited = (uint32_t*)c->visited.p;
+    CU(cudaMemsetAsync(sm.err, 0, sizeof(int), c->stream));
+    kern<<<grid, MM_TILE, smem, c->stream>>>(a, d_bytes, d_offs, d_out, sp, sm.err);
+    c->launches++;
+    CU(cudaGetLastError());
+    if (!any_bt) return RGX_OK;     // nothing can overflow: no readback, the call stays asynchronous
+    if ((rc = read_small(c, 64))) return rc;
+    const int e = *(int*)c->h_small;
+    if (e == 0) return RGX_OK;
+    if (attempt == 1 || !(e & (ERR_STACK | ERR_CSTACK))) { set_error("device engine scratch exhausted:" + err_bits(e)); return RGX_ENOMEM; }
+  }
+  return RGX_OK;
+}
+
 extern "C" {
 
 int rgx_ctx_create(int32_t device, rgx_ctx** out) {
@@ -230,7 +330,7 @@ void rgx_ctx_destroy(rgx_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->stack, &c->cstack, &c->visited, &c->small, &c->in_bytes, &c->in_offs, &c->out_flag, &c->out_rec,
-                    &c->out_reps, &c->out_aux, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
+                    &c->out_reps, &c->out_aux, &c->mm_tab, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
                     &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase, &c->ch_segsel, &c->ch_segreps, &c->ch_entry, &c->ch_tile};
   for (DevBuf* b : bufs) free_buf(*b);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -352,7 +452,10 @@ static int batch_dev(rgx_ctx* c, const rgx_program* p, int what, const uint8_t* 
 }
 
 int rgx_match_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t n, uint8_t* d_out) {
-  return batch_dev(c, p, 0, d_bytes, d_offs, n, d_out, nullptr);
+  if (!p) { set_error("null context/program"); return RGX_EINVAL; }
+  if (n == 0) return RGX_OK;
+  const uint64_t pf[2] = {0, n};
+  return match_multi_dev<unsigned long long>(c, &p, 1, d_bytes, (const unsigned long long*)d_offs, pf, d_out);
 }
 int rgx_find_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes, const uint64_t* d_offs, uint64_t n,
                        uint8_t* d_found, int64_t* d_out) {
@@ -394,6 +497,39 @@ int rgx_find_batch(rgx_ctx* c, const rgx_program* p, const uint8_t* bytes, const
                    int64_t* out) {
   if (n && !out) { set_error("null argument"); return RGX_EINVAL; }
   return batch_host(c, p, 1, bytes, offs, n, found, out);
+}
+
+int rgx_match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_progs, const uint8_t* d_bytes, const uint32_t* d_offs32,
+                        const uint64_t* prog_first, uint8_t* d_out) {
+  return match_multi_dev<uint32_t>(c, progs, n_progs, d_bytes, d_offs32, prog_first, d_out);
+}
+
+int rgx_match_multi(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_progs, const uint8_t* bytes, const uint64_t* offs,
+                    const uint64_t* prog_first, uint8_t* out) {
+  if (!c || !progs || !prog_first || !offs || n_progs == 0) { set_error("null argument"); return RGX_EINVAL; }
+  const uint64_t i0 = prog_first[0], n = prog_first[n_progs] - i0;
+  if (n == 0) return RGX_OK;
+  if (!out) { set_error("null argument"); return RGX_EINVAL; }
+  const uint64_t base = offs[i0], total = offs[i0 + n] - base;
+  if (total > 0xFFFFFFF0ull) { set_error("rgx_match_multi: a batch holds at most 4 GiB of input bytes (32-bit shard-relative offsets); split it"); return RGX_EINVAL; }
+  CU(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = ensure(c, c->in_bytes, total + 16))) return rc;
+  if ((rc = ensure(c, c->in_offs, (n + 1) * 4))) return rc;
+  if ((rc = ensure(c, c->out_flag, n))) return rc;
+  // the ABI's 64-bit offsets become 32-bit offsets relative to the batch's first byte
+  std::vector<uint32_t> o32(n + 1);
+  for (uint64_t i = 0; i <= n; i++) o32[i] = (uint32_t)(offs[i0 + i] - base);
+  std::vector<uint64_t> pf(n_progs + 1);
+  for (uint32_t p = 0; p <= n_progs; p++) pf[p] = prog_first[p] - i0;
+  if (total) CU(cudaMemcpyAsync(c->in_bytes.p, bytes + base, total, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(c->in_offs.p, o32.data(), (n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  rc = match_multi_dev<uint32_t>(c, progs, n_progs, (const uint8_t*)c->in_bytes.p, (const uint32_t*)c->in_offs.p, pf.data(), (uint8_t*)c->out_flag.p);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->out_flag.p, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RGX_OK;
 }
 
 }  // extern "C"

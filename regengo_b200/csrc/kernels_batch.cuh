@@ -62,4 +62,113 @@ __global__ void __launch_bounds__(256) batch_kernel(const DevMeta m, const uint3
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// match_multi_kernel -- batched MatchBytes for MANY patterns in one launch (BASELINE.json configs[3]: the curated
+// suite over 100 M short inputs).  The batch is packed bytes[] + offsets[n+1]; the inputs of program p are the index
+// range [prog_first[p], prog_first[p+1]).  Work is cut into ITEMS = runs of consecutive 256-input tiles of one
+// program; a CTA stages its program's image once (TMA bulk copy) and then, per tile:
+//   * reads the tile's 257 offsets with one coalesced load (32-bit shard-relative offsets on the batch path),
+//   * copies the tile's bytes -- one contiguous span of the packed buffer -- into shared memory with 16-byte loads,
+//   * thread t runs the pattern's engine on its input OUT OF SHARED MEMORY (no per-byte global loads, no sector
+//     waste on 12-byte inputs) and writes its flag byte; a warp's 32 flags are one 32-byte store.
+// One thread still runs one machine sequentially, so restart order and the skip-restart rule hold by
+// construction.  A tile whose bytes do not fit the staging buffer (long inputs) reads global memory directly.
+constexpr uint32_t MM_TILE = 256;                 // inputs per tile = threads per CTA
+constexpr uint32_t MM_TILE_BYTES = 24 * 1024;     // staging buffer for a tile's bytes
+constexpr uint32_t MM_IMAGE_BYTES = 40 * 1024;    // images up to this size are staged; larger ones are read from L2
+
+static_assert(sizeof(DevMeta) % 4 == 0, "DevMeta is copied word by word");
+struct MultiArgs {
+  const DevMeta* metas;              // [n_progs]
+  const uint32_t* const* images;     // [n_progs] device image words
+  const uint32_t* item_base;         // [n_progs + 1] first item of each program
+  const unsigned long long* prog_first;   // [n_progs + 1] first input of each program
+  uint32_t n_progs, n_items, tiles_per_item;
+};
+
+template <typename OFFT>
+__global__ void max_len_multi_kernel(const OFFT* __restrict__ offs, uint64_t n, unsigned long long* out) {
+  unsigned long long mx = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long d = (unsigned long long)(offs[i + 1] - offs[i]);
+    mx = d > mx ? d : mx;
+  }
+  for (int o = 16; o; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, mx, o); mx = v > mx ? v : mx; }
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
+template <typename OFFT>
+__global__ void __launch_bounds__(MM_TILE) match_multi_kernel(const MultiArgs a, const uint8_t* __restrict__ bytes,
+                                                              const OFFT* __restrict__ offs, uint8_t* __restrict__ flag,
+                                                              const ScratchPlan sp, int* err) {
+  extern __shared__ __align__(16) uint32_t mm_smem[];       // [image | tile bytes]
+  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ DevMeta sm_meta;
+  __shared__ unsigned long long toffs[MM_TILE + 1];
+  uint32_t* simg = mm_smem;
+  uint8_t* tbytes = reinterpret_cast<uint8_t*>(mm_smem) + MM_IMAGE_BYTES;
+
+  Scratch sc;
+  sc.stack = sp.stack; sc.cstack = sp.cstack; sc.visited = sp.visited;
+  sc.stack_cap = sp.stack_cap; sc.cstack_cap = sp.cstack_cap; sc.visited_words = sp.visited_words;
+  sc.stride = sp.stride; sc.tid = blockIdx.x * blockDim.x + threadIdx.x;
+
+  int cur_prog = -1;
+  const uint32_t* img = nullptr;
+  for (uint32_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    // which program: the last p with item_base[p] <= item
+    uint32_t lo = 0, hi = a.n_progs;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.item_base[mid] <= item) lo = mid; else hi = mid; }
+    const uint32_t p = lo;
+    if ((int)p != cur_prog) {
+      __syncthreads();   // everyone is done with the previous image / meta
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(a.metas + p);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm_meta);
+      for (uint32_t k = threadIdx.x; k < sizeof(DevMeta) / 4; k += MM_TILE) dst[k] = src[k];
+      __syncthreads();
+      img = a.images[p];
+      if (sm_meta.image_words * 4u <= MM_IMAGE_BYTES) {
+        stage_image_tma(simg, img, sm_meta.image_words, &mbar);
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
+        img = simg;
+      }
+      cur_prog = (int)p;
+    }
+    const DevMeta& m = sm_meta;
+    const unsigned long long in_first = a.prog_first[p], in_end = a.prog_first[p + 1];
+    const unsigned long long t0 = (unsigned long long)(item - a.item_base[p]) * a.tiles_per_item;
+    for (uint32_t tt = 0; tt < a.tiles_per_item; tt++) {
+      const unsigned long long i0 = in_first + (t0 + tt) * MM_TILE;
+      if (i0 >= in_end) break;
+      const uint32_t nin = (uint32_t)min((unsigned long long)MM_TILE, in_end - i0);
+      __syncthreads();   // the previous tile's bytes are no longer read
+      if (threadIdx.x < nin) toffs[threadIdx.x] = (unsigned long long)offs[i0 + threadIdx.x];
+      if (threadIdx.x == 0) toffs[nin] = (unsigned long long)offs[i0 + nin];
+      __syncthreads();
+      const unsigned long long b0 = toffs[0], b1 = toffs[nin];
+      const uintptr_t addr0 = reinterpret_cast<uintptr_t>(bytes + b0) & ~(uintptr_t)15;
+      const unsigned long long span = reinterpret_cast<uintptr_t>(bytes + b1) - addr0;   // bytes from the aligned base to the tile's end
+      const bool staged = span + 16 <= MM_TILE_BYTES;
+      if (staged) {
+        // (reads stay inside the 16-byte chunks that hold the tile's first and last byte)
+        const uint4* g = reinterpret_cast<const uint4*>(addr0);
+        uint4* d = reinterpret_cast<uint4*>(tbytes);
+        const uint32_t nvec = b1 > b0 ? (uint32_t)((span - 1) >> 4) + 1u : 0u;
+        for (uint32_t k = threadIdx.x; k < nvec; k += MM_TILE) d[k] = g[k];
+      }
+      __syncthreads();
+      if (threadIdx.x < nin) {
+        const unsigned long long b = toffs[threadIdx.x];
+        const int64_t l = (int64_t)(toffs[threadIdx.x + 1] - b);
+        const uint8_t* in = staged ? tbytes + (reinterpret_cast<uintptr_t>(bytes + b) - addr0) : bytes + b;
+        int r;
+        if (m.match_engine == MATCH_THOMPSON) r = thompson_match(m, img, in, l);
+        else r = bt_machine<MODE_MATCH>(m, img, in, l, 0, nullptr, sc, err);
+        flag[i0 + threadIdx.x] = (uint8_t)r;
+      }
+    }
+  }
+}
+
 }  // namespace rgx

@@ -334,3 +334,38 @@ def test_find_all_at_scale_properties():
     assert t3 == tot and n_rec.value == ref_reps.numel()
     assert np.array_equal(h_out[: n_rec.value * nc], ref_recs.cpu().numpy())
     assert np.array_equal(h_reps[: n_rec.value].astype(np.int64), ref_reps.cpu().numpy().astype(np.int64))
+
+
+def test_match_multi_one_launch_for_the_suite():
+    """rgx_match_multi: every corpus pattern's inputs in ONE packed batch and one launch; flags equal the oracle's
+    MatchBytes per pattern.  Tiles of 256 inputs are cut at program boundaries; some programs get no input at all,
+    one gets inputs longer than the tile staging buffer (global-memory fallback), some inputs are empty."""
+    pats, oracles, inputs, first = [], [], [], [0]
+    k = 0
+    for ent in CORPUS["e2e"] + CORPUS["curated"]:
+        if ent["pattern"] in UNSUPPORTED:
+            continue
+        p, o = pair(ent["pattern"])
+        pats.append(p); oracles.append(o)
+        mine = [c["input"].encode("utf-8") for c in ent["cases"]]
+        if k % 7 != 3:                                  # every seventh program has no inputs
+            mine += synth.mutate_inputs([c["input"] for c in ent["cases"]], 150 + 37 * (k % 11), stream=1000 + k)
+            mine += [b"", b"a"]
+        else:
+            mine = []
+        if k == 5:
+            mine += [b"x" * 30000 + mine[0] + b"y" * 7, b"z" * 100]   # one tile's bytes exceed the staging buffer
+        inputs += mine
+        first.append(len(inputs))
+        k += 1
+    data, offs = rg.pack_inputs(inputs)
+    got = rg.match_multi(pats, data, offs, first)
+    assert got.shape[0] == len(inputs) and len(pats) >= 230
+    for j, o in enumerate(oracles):
+        lo, hi = first[j], first[j + 1]
+        if hi > lo:
+            exp = o.match_batch(data, offs[lo:hi + 1])
+            assert np.array_equal(got[lo:hi], exp), (pats[j].pattern, [inputs[lo + i] for i in np.nonzero(got[lo:hi] != exp)[0][:3]])
+    # a sub-range of the program table (prog_first[0] > 0) gives the same flags
+    sub = rg.match_multi(pats[10:20], data, offs, first[10:21])
+    assert np.array_equal(sub, got[first[10]:first[20]])
