@@ -216,7 +216,7 @@ static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t
   // items: runs of tiles of one program, sized so that a few CTAs per SM cover the batch
   uint64_t total_tiles = 0;
   for (uint32_t p = 0; p < n_progs; p++) total_tiles += (prog_first[p + 1] - prog_first[p] + MM_TILE - 1) / MM_TILE;
-  const uint64_t target_items = (uint64_t)c->sm_count * 16;
+  const uint64_t target_items = (uint64_t)c->sm_count * 96;   // fine enough that the slowest program's items do not form a tail
   const uint32_t tiles_per_item = (uint32_t)std::max<uint64_t>(1, (total_tiles + target_items - 1) / target_items);
   std::vector<uint32_t> item_base(n_progs + 1, 0);
   for (uint32_t p = 0; p < n_progs; p++) {
@@ -225,7 +225,7 @@ static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t
     if (item_base[p] + items > 0x7FFFFFFFull) { set_error("rgx_match_multi: batch too large"); return RGX_EINVAL; }
     item_base[p + 1] = item_base[p] + (uint32_t)items;
   }
-  const size_t off_ptr = (size_t)n_progs * sizeof(DevMeta), off_item = off_ptr + (size_t)n_progs * 8,
+  const size_t off_ptr = ((size_t)n_progs * sizeof(DevMeta) + 7) & ~(size_t)7, off_item = off_ptr + (size_t)n_progs * 8,
                off_first = (off_item + (size_t)(n_progs + 1) * 4 + 7) & ~(size_t)7, tab_bytes = off_first + (size_t)(n_progs + 1) * 8;
   std::vector<uint8_t> tab(tab_bytes, 0);
   for (uint32_t p = 0; p < n_progs; p++) {
@@ -248,18 +248,41 @@ static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t
   a.item_base = (const uint32_t*)((const char*)c->mm_tab.p + off_item);
   a.prog_first = (const unsigned long long*)((const char*)c->mm_tab.p + off_first);
   a.n_progs = n_progs; a.n_items = item_base[n_progs]; a.tiles_per_item = tiles_per_item;
+  a.image_bytes = 16;
+  for (uint32_t p = 0; p < n_progs; p++) {
+    const uint32_t b = ims[p]->meta.match_words * 4u;
+    if (b <= MM_IMAGE_BYTES) a.image_bytes = std::max(a.image_bytes, (b + 15u) & ~15u);
+  }
 
   Small sm = small_of(c);
-  uint64_t max_len = 0;
-  if (any_bt) {   // sizes the per-thread backtracking scratch; Thompson-only batches need none
-    CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
-    max_len_multi_kernel<OFFT><<<std::max(1, c->sm_count * 4), 256, 0, c->stream>>>(d_offs + prog_first[0], n - prog_first[0], sm.slots);
+  const size_t smem = (size_t)a.image_bytes + MM_TILE_BYTES;
+  // first try: stack and visited bits in local memory (no sizing pass, no scratch)
+  {
+    auto kern = match_multi_kernel<OFFT, true>;
+    int grid = 0;
+    if ((rc = occupancy_grid(c, kern, MM_TILE, smem, &grid))) return rc;
+    if ((uint32_t)grid > a.n_items) grid = (int)a.n_items;
+    ScratchPlan sp;
+    std::memset(&sp, 0, sizeof sp);
+    sp.stride = (uint32_t)grid * MM_TILE;
+    CU(cudaMemsetAsync(sm.err, 0, sizeof(int), c->stream));
+    kern<<<grid, MM_TILE, smem, c->stream>>>(a, d_bytes, d_offs, d_out, sp, sm.err);
     c->launches++;
-    if ((rc = read_small(c, 256))) return rc;
-    max_len = *(unsigned long long*)((char*)c->h_small + 64);
+    CU(cudaGetLastError());
+    if (!any_bt) return RGX_OK;     // nothing can overflow: no readback, the call stays asynchronous
+    if ((rc = read_small(c, 64))) return rc;
+    const int e = *(int*)c->h_small;
+    if (e == 0) return RGX_OK;
+    if (e & ~(ERR_STACK | ERR_VISITED)) { set_error("device engine failure:" + err_bits(e)); return RGX_ENOMEM; }
   }
-  const size_t smem = MM_IMAGE_BYTES + MM_TILE_BYTES;
-  auto kern = match_multi_kernel<OFFT>;
+  // some input outgrew the local arrays: the whole batch again with global scratch sized for the longest input
+  uint64_t max_len = 0;
+  CU(cudaMemsetAsync(c->small.p, 0, 256, c->stream));
+  max_len_multi_kernel<OFFT><<<std::max(1, c->sm_count * 4), 256, 0, c->stream>>>(d_offs + prog_first[0], n - prog_first[0], sm.slots);
+  c->launches++;
+  if ((rc = read_small(c, 256))) return rc;
+  max_len = *(unsigned long long*)((char*)c->h_small + 64);
+  auto kern = match_multi_kernel<OFFT, false>;
   int grid = 0;
   if ((rc = occupancy_grid(c, kern, MM_TILE, smem, &grid))) return rc;
   if ((uint32_t)grid > a.n_items) grid = (int)a.n_items;
@@ -283,7 +306,6 @@ static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t
     kern<<<grid, MM_TILE, smem, c->stream>>>(a, d_bytes, d_offs, d_out, sp, sm.err);
     c->launches++;
     CU(cudaGetLastError());
-    if (!any_bt) return RGX_OK;     // nothing can overflow: no readback, the call stays asynchronous
     if ((rc = read_small(c, 64))) return rc;
     const int e = *(int*)c->h_small;
     if (e == 0) return RGX_OK;
@@ -547,6 +569,7 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   std::string s = "{";
   auto kv = [&](const char* k, long long v) { if (s.size() > 1) s += ", "; s += "\""; s += k; s += "\": "; s += std::to_string(v); };
   kv("image_bytes", (long long)m.image_words * 4);
+  kv("match_image_bytes", (long long)m.match_words * 4);
   kv("find_engine", m.find_engine);
   kv("gen_kind", m.gen_kind);
   kv("prefix_len", m.prefix_len);

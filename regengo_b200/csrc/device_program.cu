@@ -120,6 +120,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     w.insert(w.end(), pairs.begin(), pairs.end());
   }
   align4();
+  m.match_words = (uint32_t)w.size();   // everything MatchBytes reads lies before this point
 
   // TDFA tables
   Bits256 first;

@@ -35,6 +35,7 @@ enum LinKind : uint32_t { LIN_CAP = 0, LIN_LIT = 1, LIN_CLS = 2, LIN_LOOP = 3, L
 struct DevMeta {
   int32_t n_inst, start, num_cap, flags, prefix, match_engine, find_engine;
   uint32_t image_words;        // multiple of 4
+  uint32_t match_words;        // multiple of 4: the leading part of the image that the MatchBytes engines read
   uint32_t off_inst, off_cls, off_th_eps, off_th_cond, off_rng_idx, off_rng_pairs;
   uint32_t off_t_trans, off_t_accept, off_t_alist_off, off_t_alist, off_t_init, off_first;
   // scan6 walk image (kernels_scan6.cuh; w6_ok = 0: absent): the contiguous sub-range [w6_off, w6_off + w6_words) of the

@@ -66,16 +66,23 @@ __global__ void __launch_bounds__(256) batch_kernel(const DevMeta m, const uint3
 // match_multi_kernel -- batched MatchBytes for MANY patterns in one launch (BASELINE.json configs[3]: the curated
 // suite over 100 M short inputs).  The batch is packed bytes[] + offsets[n+1]; the inputs of program p are the index
 // range [prog_first[p], prog_first[p+1]).  Work is cut into ITEMS = runs of consecutive 256-input tiles of one
-// program; a CTA stages its program's image once (TMA bulk copy) and then, per tile:
-//   * reads the tile's 257 offsets with one coalesced load (32-bit shard-relative offsets on the batch path),
-//   * copies the tile's bytes -- one contiguous span of the packed buffer -- into shared memory with 16-byte loads,
-//   * thread t runs the pattern's engine on its input OUT OF SHARED MEMORY (no per-byte global loads, no sector
+// program; a CTA stages its program's image once (TMA bulk copy) and then every warp, 32 inputs at a time:
+//   * reads the offsets with one coalesced load (32-bit shard-relative offsets on the batch path),
+//   * copies the 32 inputs' bytes -- one contiguous span of the packed buffer -- into shared memory with 16-byte loads,
+//   * lane t runs the pattern's engine on its input OUT OF SHARED MEMORY (no per-byte global loads, no sector
 //     waste on 12-byte inputs) and writes its flag byte; a warp's 32 flags are one 32-byte store.
+//   * LOCAL: the goto-machine's backtrack stack and visited bits live in per-thread LOCAL memory, which the L1 caches
+//     write-back -- a push/pop costs an L1 hit instead of an L2 round trip to the interleaved global scratch.  An
+//     input that outgrows the local arrays flags ERR_STACK / ERR_VISITED and the host re-runs the batch with the
+//     global scratch sized for the provable worst case (LOCAL = false).
 // One thread still runs one machine sequentially, so restart order and the skip-restart rule hold by
 // construction.  A tile whose bytes do not fit the staging buffer (long inputs) reads global memory directly.
 constexpr uint32_t MM_TILE = 256;                 // inputs per tile = threads per CTA
-constexpr uint32_t MM_TILE_BYTES = 24 * 1024;     // staging buffer for a tile's bytes
+constexpr uint32_t MM_WARP_BYTES = 2048;          // per-warp staging buffer for the bytes of 32 inputs
+constexpr uint32_t MM_TILE_BYTES = (MM_TILE / 32) * MM_WARP_BYTES;
 constexpr uint32_t MM_IMAGE_BYTES = 40 * 1024;    // images up to this size are staged; larger ones are read from L2
+constexpr uint32_t MM_LSTACK = 256;               // backtrack-stack entries kept in (L1-cached, write-back) local memory
+constexpr uint32_t MM_LVISITED = 640;             // words of the memoisation bit-vector kept in local memory
 
 static_assert(sizeof(DevMeta) % 4 == 0, "DevMeta is copied word by word");
 struct MultiArgs {
@@ -84,6 +91,7 @@ struct MultiArgs {
   const uint32_t* item_base;         // [n_progs + 1] first item of each program
   const unsigned long long* prog_first;   // [n_progs + 1] first input of each program
   uint32_t n_progs, n_items, tiles_per_item;
+  uint32_t image_bytes;              // shared memory reserved for a staged image (the largest one, at most MM_IMAGE_BYTES)
 };
 
 template <typename OFFT>
@@ -97,21 +105,26 @@ __global__ void max_len_multi_kernel(const OFFT* __restrict__ offs, uint64_t n, 
   if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
 }
 
-template <typename OFFT>
+template <typename OFFT, bool LOCAL>
 __global__ void __launch_bounds__(MM_TILE) match_multi_kernel(const MultiArgs a, const uint8_t* __restrict__ bytes,
                                                               const OFFT* __restrict__ offs, uint8_t* __restrict__ flag,
                                                               const ScratchPlan sp, int* err) {
   extern __shared__ __align__(16) uint32_t mm_smem[];       // [image | tile bytes]
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ DevMeta sm_meta;
-  __shared__ unsigned long long toffs[MM_TILE + 1];
   uint32_t* simg = mm_smem;
-  uint8_t* tbytes = reinterpret_cast<uint8_t*>(mm_smem) + MM_IMAGE_BYTES;
+  uint8_t* tbytes = reinterpret_cast<uint8_t*>(mm_smem) + a.image_bytes;
 
   Scratch sc;
   sc.stack = sp.stack; sc.cstack = sp.cstack; sc.visited = sp.visited;
   sc.stack_cap = sp.stack_cap; sc.cstack_cap = sp.cstack_cap; sc.visited_words = sp.visited_words;
   sc.stride = sp.stride; sc.tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint2 lstack[LOCAL ? MM_LSTACK : 1];
+  uint32_t lvisited[LOCAL ? MM_LVISITED : 1];
+  if (LOCAL) {
+    sc.stack = lstack; sc.visited = lvisited; sc.cstack = nullptr;
+    sc.stack_cap = MM_LSTACK; sc.cstack_cap = 0; sc.visited_words = MM_LVISITED; sc.stride = 1; sc.tid = 0;
+  }
 
   int cur_prog = -1;
   const uint32_t* img = nullptr;
@@ -127,8 +140,8 @@ __global__ void __launch_bounds__(MM_TILE) match_multi_kernel(const MultiArgs a,
       for (uint32_t k = threadIdx.x; k < sizeof(DevMeta) / 4; k += MM_TILE) dst[k] = src[k];
       __syncthreads();
       img = a.images[p];
-      if (sm_meta.image_words * 4u <= MM_IMAGE_BYTES) {
-        stage_image_tma(simg, img, sm_meta.image_words, &mbar);
+      if (sm_meta.match_words * 4u <= a.image_bytes) {
+        stage_image_tma(simg, img, sm_meta.match_words, &mbar);
         __syncthreads();
         if (threadIdx.x == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&mbar)) : "memory");
         img = simg;
@@ -137,35 +150,47 @@ __global__ void __launch_bounds__(MM_TILE) match_multi_kernel(const MultiArgs a,
     }
     const DevMeta& m = sm_meta;
     const unsigned long long in_first = a.prog_first[p], in_end = a.prog_first[p + 1];
-    const unsigned long long t0 = (unsigned long long)(item - a.item_base[p]) * a.tiles_per_item;
-    for (uint32_t tt = 0; tt < a.tiles_per_item; tt++) {
-      const unsigned long long i0 = in_first + (t0 + tt) * MM_TILE;
-      if (i0 >= in_end) break;
-      const uint32_t nin = (uint32_t)min((unsigned long long)MM_TILE, in_end - i0);
-      __syncthreads();   // the previous tile's bytes are no longer read
-      if (threadIdx.x < nin) toffs[threadIdx.x] = (unsigned long long)offs[i0 + threadIdx.x];
-      if (threadIdx.x == 0) toffs[nin] = (unsigned long long)offs[i0 + nin];
-      __syncthreads();
-      const unsigned long long b0 = toffs[0], b1 = toffs[nin];
+    const unsigned long long item_first = in_first + (unsigned long long)(item - a.item_base[p]) * a.tiles_per_item * MM_TILE;
+    const unsigned long long item_end = min(in_end, item_first + (unsigned long long)a.tiles_per_item * MM_TILE);
+    // Each WARP walks the item's inputs 32 at a time on its own (no block barrier in this loop: a slow input holds
+    // up its warp, not the other seven): offsets by one coalesced load, the 32 inputs' bytes -- one contiguous span
+    // -- into the warp's staging buffer with 16-byte loads, one machine per lane out of shared memory.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* wbytes = tbytes + (size_t)warp * MM_WARP_BYTES;
+    for (unsigned long long i0 = item_first + (unsigned long long)warp * 32; i0 < item_end; i0 += MM_TILE) {
+      const uint32_t nin = (uint32_t)min(32ull, item_end - i0);
+      const unsigned long long b = (uint32_t)lane < nin ? (unsigned long long)offs[i0 + lane] : 0ull;
+      const unsigned long long e_last = (unsigned long long)offs[i0 + nin];
+      const unsigned long long b_next = __shfl_down_sync(0xFFFFFFFFu, b, 1);
+      const unsigned long long e = (uint32_t)lane + 1 < nin ? b_next : e_last;
+      const unsigned long long b0 = __shfl_sync(0xFFFFFFFFu, b, 0), b1 = e_last;
       const uintptr_t addr0 = reinterpret_cast<uintptr_t>(bytes + b0) & ~(uintptr_t)15;
       const unsigned long long span = reinterpret_cast<uintptr_t>(bytes + b1) - addr0;   // bytes from the aligned base to the tile's end
-      const bool staged = span + 16 <= MM_TILE_BYTES;
+      const bool staged = span + 16 <= MM_WARP_BYTES;
+      __syncwarp();   // the previous tile's bytes are no longer read
       if (staged) {
         // (reads stay inside the 16-byte chunks that hold the tile's first and last byte)
         const uint4* g = reinterpret_cast<const uint4*>(addr0);
-        uint4* d = reinterpret_cast<uint4*>(tbytes);
+        uint4* d = reinterpret_cast<uint4*>(wbytes);
         const uint32_t nvec = b1 > b0 ? (uint32_t)((span - 1) >> 4) + 1u : 0u;
-        for (uint32_t k = threadIdx.x; k < nvec; k += MM_TILE) d[k] = g[k];
+        for (uint32_t k = lane; k < nvec; k += 32) d[k] = g[k];
       }
-      __syncthreads();
-      if (threadIdx.x < nin) {
-        const unsigned long long b = toffs[threadIdx.x];
-        const int64_t l = (int64_t)(toffs[threadIdx.x + 1] - b);
-        const uint8_t* in = staged ? tbytes + (reinterpret_cast<uintptr_t>(bytes + b) - addr0) : bytes + b;
+      __syncwarp();
+      if ((uint32_t)lane < nin) {
+        const int64_t l = (int64_t)(e - b);
+        const uint8_t* in = staged ? wbytes + (reinterpret_cast<uintptr_t>(bytes + b) - addr0) : bytes + b;
         int r;
         if (m.match_engine == MATCH_THOMPSON) r = thompson_match(m, img, in, l);
-        else r = bt_machine<MODE_MATCH>(m, img, in, l, 0, nullptr, sc, err);
-        flag[i0 + threadIdx.x] = (uint8_t)r;
+        else {
+          if (LOCAL && (m.flags & F_MATCH_MEMO)) {
+            // only the words this input needs are cleared per restart (compiler.go:812-818: numInst * (l+1) bits)
+            const unsigned long long words = ((unsigned long long)m.n_inst * (unsigned long long)(l + 1) + 31) / 32;
+            sc.visited_words = (uint32_t)min(words, (unsigned long long)MM_LVISITED);
+            if (words > MM_LVISITED) atomicOr(err, ERR_VISITED);
+          }
+          r = bt_machine<MODE_MATCH>(m, img, in, l, 0, nullptr, sc, err);
+        }
+        flag[i0 + lane] = (uint8_t)r;
       }
     }
   }
