@@ -104,6 +104,9 @@ int rgx_ctx_create(int32_t device, rgx_ctx** out);
 void rgx_ctx_destroy(rgx_ctx* c);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 int64_t rgx_ctx_launches(const rgx_ctx* c);
+/* Statistics of the last call on this context.  which = 0: chunks of the last FindReader call that were replayed by
+ * the sequential form of the chase instead of the lane-parallel one (-1: unknown `which`). */
+int64_t rgx_ctx_stat(const rgx_ctx* c, int32_t which);
 /* Upload granularity of the host-buffer FindAll (rgx_find_all / rgx_find_all_rle): inputs of at least two
  * chunks are uploaded chunk by chunk while earlier chunks are scanned (default 256 MiB; a multiple of
  * 32 KiB, at least 64 KiB). */

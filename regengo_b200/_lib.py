@@ -39,6 +39,7 @@ _SIGS = {
     "rgx_ctx_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
     "rgx_ctx_destroy": (None, [_P]),
     "rgx_ctx_launches": (C.c_int64, [_P]),
+    "rgx_ctx_stat": (C.c_int64, [_P, C.c_int32]),
     "rgx_ctx_set_chunk_bytes": (C.c_int, [_P, C.c_uint64]),
     "rgx_ctx_enable_timing": (C.c_int, [_P, C.c_int32]),
     "rgx_ctx_last_timing": (C.c_int, [_P, C.POINTER(C.c_float)]),

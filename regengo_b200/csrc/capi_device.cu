@@ -49,6 +49,7 @@ struct rgx_ctx {
   void* h_small = nullptr;  // pinned, 4 KiB
   uint32_t fa_K = 128;      // slab capacity per segment, doubled on overflow
   uint32_t fa_stack_cap = 256;
+  int64_t stat_seq_chunks = 0;   // FindReader: chunks of the last call that took the sequential replay (statistics)
   int chain_first_batch = 8;  // chain passes queued before the first readback (adapts to the data)
   // optional per-phase timing of the last FindAll (CUDA events on the launching stream)
   bool timing = false;
@@ -365,6 +366,7 @@ void rgx_ctx_destroy(rgx_ctx* c) {
 }
 
 int64_t rgx_ctx_launches(const rgx_ctx* c) { return c ? c->launches : 0; }
+int64_t rgx_ctx_stat(const rgx_ctx* c, int32_t which) { return c && which == 0 ? c->stat_seq_chunks : -1; }
 
 int rgx_ctx_set_chunk_bytes(rgx_ctx* c, uint64_t bytes) {
   if (!c || bytes < (1u << 16) || (bytes & 0x7FFFu)) { set_error("rgx_ctx_set_chunk_bytes: need a multiple of 32 KiB, at least 64 KiB"); return RGX_EINVAL; }

@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
     const uint8_t* sp = abuf + base_a;                    // range base; every position below is relative to it
     asm volatile("" : "+l"(sp));                          // (opaque to the compiler: keep it in registers, do not re-derive it)
     const uint32_t range_bytes = n_rseg * SEG2_BYTES;
-    const bool interior = base_a >= mis && base_a + range_bytes <= end_a && base_a + range_bytes + 4 <= load_end;
     const uint64_t avail64 = load_end - base_a;
     const uint32_t lim = avail64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)avail64;   // bytes readable from sp
     const uint32_t lim_eot = avail64 <= 0xFFFFFFF0ull ? lim : 0xFFFFFFFFu;            // position that means "the buffer's last byte was consumed"

@@ -195,13 +195,15 @@ __device__ __forceinline__ int reader_attempt(const DevMeta& m, const uint32_t* 
 // d_stream[0:len) = the shard; entry i describes the attempt at shard position i with the whole shard visible
 __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                 const uint8_t* __restrict__ d_stream, const uint64_t len,
-                                                                uint16_t* __restrict__ table, const ScratchPlan sp, int* err) {
+                                                                uint16_t* __restrict__ table, const ScratchPlan sp, int* err,
+                                                                int* slow_flag) {
   extern __shared__ __align__(16) uint32_t smem_img[];
   __shared__ __align__(8) unsigned long long mbar;
   const uint32_t* img = gimg;
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
   const uint32_t* first = img + m.off_first;
+  bool any_slow = false;
   const uint64_t n_units = (len + 63) / 64;     // 64 consecutive positions per thread
   for (uint64_t u = sc.tid; u < n_units; u += sp.stride) {
     const uint64_t p0 = u * 64;
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
         entry = (r7 << 8) | (nx >= (int64_t)RT_SLOW_VAL || nx < 1 ? RT_SLOW_VAL : (uint32_t)nx);
       }
       ent[j] = (uint16_t)entry;
+      any_slow = any_slow || ((entry >> 8) & 0x7Fu) == RT_SLOW_REACH || (entry & 0xFFu) == RT_SLOW_VAL;
     }
     auto entry_of = [&](const uint32_t j) -> uint32_t {
       if ((cand >> j) & 1ull) return ent[j];
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
       for (uint32_t j = 0; j < nb; j++) table[p0 + j] = (uint16_t)entry_of(j);
     }
   }
+  if (any_slow) *slow_flag = 1;   // some entry says "decide inline": the chase keeps to the sequential form
 }
 
 // The same table for a STRAIGHT-LINE program (device_program.cu: sl_*), bit-parallel: a thread owns 64
@@ -387,6 +391,147 @@ __device__ __forceinline__ int64_t warp_index_of_text(const uint8_t* hay, int64_
   return ns;
 }
 
+// bytes.Index(hay[from:], hay[ns:ns+nl]) by ONE lane, testing only positions the table does not rule out: an entry
+// {no match, reach 1, next > 1} is a byte outside the first-byte set, and so are the next - 1 bytes after it; the match
+// text starts with a byte of that set.
+__device__ __forceinline__ int64_t table_index_of_text(const uint8_t* hay, const uint16_t* tab, int64_t from, int64_t ns, int64_t nl) {
+  for (int64_t q = from; q < ns;) {
+    const uint32_t e = tab[q];
+    if (!(e & 0x8000u) && ((e >> 8) & 0x7Fu) == 1u && (e & 0xFFu) > 1u) { q += (int64_t)(e & 0xFFu); continue; }
+    int64_t j = 0;
+    while (j < nl && hay[q + j] == hay[ns + j]) j++;
+    if (j == nl) return q;
+    q++;
+  }
+  return ns;
+}
+
+// The chase of one chunk by the 32 lanes of a warp, each over its own range of the chunk (no entry of the table says
+// "decide inline": the caller checked).
+//
+// SYNC POINTS.  Call extent(a) = max(reach, len-or-next) of the entry at a: the attempt at a looks no further than
+// a + extent(a), and whatever the replay does at a -- fail and restart, match and continue behind the match, match
+// with the text located earlier (Q16) -- its next position is at most a + extent(a).  If every a < c has
+// a + extent(a) <= c, then c is visited by EVERY replay that starts before c: take the last visited position v < c;
+// the next one is >= c by choice of v and <= v + extent(v) <= c.  Extents are below 255 here, so a lane finds such a
+// c by scanning entries from its nominal start s with cover = s + 254.  From c on the replay depends on the past
+// only through searchPos (the end of the last match), which matters for one thing: where bytes.Index starts looking
+// for the text of the range's FIRST match.
+//   1. every lane replays [c_i, c_{i+1}) and keeps: hit count, first match (attempt start, length), last match end;
+//   2. the true searchPos entering range i is the running maximum of the last match ends before it;
+//   3. PROLOGUE of range i: while the first match's text occurs at some q in [searchPos, c_i) -- a copy that the
+//      skip-restart rule jumped over -- the reference reports the match THERE (bytes.Index), moves searchPos to
+//      q + len and searches on: that stretch [q + len, c_i) is replayed exactly (its searchPos is known), and the
+//      replay arrives at c_i again (sync point), where the first match is found once more;
+//   4. the hits are written in range order: prologue hits, then the range's own.
+//
+// All 32 lanes run ONE loop in lock-step (replay_lanes): a lane is a small state machine -- FIND (prologue: look for
+// a copy of the text), CHAIN (follow the attempts), INDEX (bytes.Index behind a match) -- and an iteration costs one
+// table entry per lane.  (Per-lane nested loops would be correct too, but the lanes of a warp then run one after
+// the other: measured 1.2 active lanes per instruction.)
+struct ChaseRange { int64_t sync, end; };
+struct ChaseOut { unsigned long long n; int64_t first_a, first_len, last_mend, spos; bool broke; };
+enum { PH_FIND = 0, PH_CHAIN = 1, PH_INDEX = 2, PH_DONE = 3 };
+
+// does hay[q:q+nl] equal hay[np:np+nl]?
+__device__ __forceinline__ bool same_text(const uint8_t* hay, int64_t q, int64_t np, int64_t nl) {
+  int64_t j = 0;
+  while (j < nl && hay[q + j] == hay[np + j]) j++;
+  return j == nl;
+}
+
+// Warp-collective.  Lane with `on`: [prologue over [pos_entry, r.sync) for the text at first_a] then [the range
+// r.sync .. r.end], as asked.  Hits go to hits[w ...] (WRITE).  out.spos = the searchPos the range's first match sees.
+template <bool WRITE>
+__device__ __forceinline__ ChaseOut replay_lanes(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* chunk, const uint16_t* tab,
+                                                 const int64_t data_len, const bool full, const int64_t L, const uint64_t cstart,
+                                                 const uint64_t k, const bool on, const bool do_prologue, const bool do_main,
+                                                 const ChaseRange r, const int64_t pos_entry, const int64_t first_a, const int64_t first_len,
+                                                 const Scratch& sc, int* err, ReaderHit* hits, unsigned long long w,
+                                                 const unsigned long long wend) {
+  ChaseOut o;
+  o.n = 0; o.first_a = -1; o.first_len = 0; o.last_mend = -1; o.spos = pos_entry; o.broke = false;
+  int phase = !on ? PH_DONE : do_prologue ? PH_FIND : do_main ? PH_CHAIN : PH_DONE;
+  bool in_main = !do_prologue, first = true;
+  int64_t pos = do_prologue ? pos_entry : r.sync;   // searchPos
+  int64_t a = r.sync;                                // attempt position (CHAIN) / match position (INDEX)
+  int64_t q = pos;                                   // scan position (FIND, INDEX)
+  int64_t cur_end = in_main ? r.end : r.sync, mlen = 0;
+  while (__any_sync(0xFFFFFFFFu, phase != PH_DONE)) {
+    if (phase == PH_FIND) {
+      if (q >= r.sync) {
+        // no (more) copy of the text before the sync point: the prologue is over
+        o.spos = pos;
+        if (do_main) { in_main = true; first = true; pos = r.sync; a = r.sync; cur_end = r.end; phase = PH_CHAIN; }
+        else phase = PH_DONE;
+      } else {
+        const uint32_t e = tab[q];
+        if (!(e & 0x8000u) && ((e >> 8) & 0x7Fu) == 1u && (e & 0xFFu) > 1u) q += (int64_t)(e & 0xFFu);   // bytes that cannot start the text
+        else if (same_text(chunk, q, first_a, first_len)) {
+          // bytes.Index finds this copy first: the match is reported here, searchPos moves behind it
+          const int64_t mend = q + first_len;
+          if (full && mend > data_len - L) { o.broke = true; phase = PH_DONE; }
+          else {
+            if (WRITE && w < wend) {
+              ReaderHit h;
+              h.search_abs = (long long)cstart + pos; h.d_true = (uint32_t)(first_a - pos); h.d_text = (uint32_t)(q - pos); h.chunk = k;
+              hits[w] = h;
+            }
+            w++; o.n++;
+            pos = mend; a = mend; cur_end = r.sync; phase = PH_CHAIN;   // replay [mend, sync) exactly
+          }
+        } else q++;
+      }
+    } else if (phase == PH_CHAIN) {
+      if (a >= cur_end) {
+        if (in_main) phase = PH_DONE;
+        else { q = pos; phase = PH_FIND; }           // back at the sync point: look for another copy behind searchPos
+      } else {
+        const uint32_t e = tab[a];
+        const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
+        if (a + (int64_t)r7 <= data_len) {
+          if (e & 0x8000u) { mlen = (int64_t)v; q = pos; phase = PH_INDEX; }
+          else a += (int64_t)v;
+        } else {
+          // the attempt would look past the end of the chunk: decide with the chunk's own limit
+          int64_t ml = 0, ns = 0, reach = 0;
+          if (reader_attempt(m, img, chunk, data_len, a, sc, err, &ml, &ns, &reach)) { mlen = ml; q = pos; phase = PH_INDEX; }
+          else if (ns > data_len) a = data_len;
+          else a = ns;
+        }
+      }
+    } else if (phase == PH_INDEX) {
+      // bytes.Index(chunk[pos:], text): first copy of the text at or behind searchPos (the match itself at the latest)
+      bool found = q >= a;
+      if (!found) {
+        const uint32_t e = tab[q];
+        if (!(e & 0x8000u) && ((e >> 8) & 0x7Fu) == 1u && (e & 0xFFu) > 1u) q += (int64_t)(e & 0xFFu);
+        else if (same_text(chunk, q, a, mlen)) found = true;
+        else q++;
+      }
+      if (found) {
+        const int64_t mstart = q < a ? q : a, mend = mstart + mlen;
+        if (full && mend > data_len - L) { o.broke = true; phase = PH_DONE; }   // too close to the boundary: next chunk's job
+        else {
+          const int64_t spos = (in_main && first) ? o.spos : pos;
+          if (in_main && first) { o.first_a = a; o.first_len = mlen; }
+          first = false;
+          if (WRITE && w < wend) {
+            ReaderHit h;
+            h.search_abs = (long long)cstart + spos; h.d_true = (uint32_t)(a - spos); h.d_text = (uint32_t)(mstart - spos); h.chunk = k;
+            hits[w] = h;
+          }
+          w++; o.n++;
+          if (in_main) o.last_mend = mend;
+          pos = mend; a = mend; phase = PH_CHAIN;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  return o;
+}
+
 // MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].  MODE 2: one pass -- list the hits of chunk j
 // at j * region (a chunk cannot hold more than `region` matches) and count them; a chunk that would overflow
 // its region sets ERR_SLAB and the caller falls back to the two-pass form.
@@ -400,13 +545,14 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
                                                                 const uint64_t first_chunk, const uint64_t n_run,
                                                                 unsigned long long* __restrict__ counts,
                                                                 const unsigned long long* __restrict__ bases, ReaderHit* __restrict__ hits,
-                                                                const uint64_t cap, const ScratchPlan sp, int* err) {
+                                                                const uint64_t cap, const ScratchPlan sp, int* err, const int* slow_flag) {
   extern __shared__ __align__(16) uint32_t smem_img[];
   __shared__ __align__(8) unsigned long long mbar;
   const uint32_t* img = gimg;
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
   const int lane = threadIdx.x & 31;
+  const bool no_slow = *slow_flag == 0;
   for (uint64_t j = sc.tid >> 5; j < n_run; j += sp.stride >> 5) {
     const uint64_t k = first_chunk + j;
     uint64_t cstart, dlen;
@@ -418,6 +564,59 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
     int64_t pos = 0;
     unsigned long long n = 0, w = MODE == 1 ? bases[j] : MODE == 2 ? j * cap : 0;
     const unsigned long long wend = MODE == 2 ? w + cap : cap;
+    // ---- the lanes split the chunk (see chase_range) ----
+    const int64_t sub = (((data_len + 31) / 32) + 63) & ~(int64_t)63;
+    if (no_slow && sub >= 1024) {
+      ChaseRange r;
+      r.sync = -1; r.end = data_len;
+      const int64_t s0 = (int64_t)lane * sub;
+      if (lane == 0) r.sync = 0;
+      else if (s0 < data_len) {
+        int64_t cover = s0 + 254;
+        const int64_t scan_end = min(data_len, s0 + sub);
+        for (int64_t a = s0; a < scan_end;) {
+          if (a >= cover) { r.sync = a; break; }
+          const uint32_t e = tab[a];
+          const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
+          cover = max(cover, a + (int64_t)max(r7, v));
+          a += (!(e & 0x8000u) && r7 == 1u && v > 1u) ? (int64_t)v : 1;   // a run of bytes that cannot start a match is one step
+        }
+      }
+      const uint32_t valid = __ballot_sync(0xFFFFFFFFu, r.sync >= 0);
+      const uint32_t higher = lane == 31 ? 0u : (valid >> (lane + 1)) << (lane + 1);
+      const int64_t nxt = __shfl_sync(0xFFFFFFFFu, r.sync, higher ? __ffs(higher) - 1 : lane);
+      if (higher) r.end = nxt;
+      const bool on = r.sync >= 0;
+      // 1. every lane replays its range (searchPos of the first match unknown yet: nothing written)
+      const ChaseOut mo = replay_lanes<false>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, on, false, true, r, 0, -1, 0, sc, err,
+                                              nullptr, 0, 0);
+      // 2. true searchPos entering each range: the last match end before it (0: none)
+      int64_t run = mo.last_mend;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xFFFFFFFFu, run, o); if (lane >= o) run = max(run, y); }
+      const int64_t prev = __shfl_up_sync(0xFFFFFFFFu, run, 1);
+      const int64_t pos_entry = lane == 0 ? 0 : max(prev, (int64_t)0);
+      // 3. prologues (count)
+      const bool pro = on && mo.first_a >= 0 && pos_entry < r.sync;
+      const ChaseOut po = replay_lanes<false>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, pro, true, false, r, pos_entry, mo.first_a,
+                                              mo.first_len, sc, err, nullptr, 0, 0);
+      // a range that ran into the deferral line ends the chunk: later ranges report nothing
+      unsigned long long cnt = po.broke ? po.n : po.n + mo.n;
+      const uint32_t bm = __ballot_sync(0xFFFFFFFFu, po.broke || mo.broke);
+      if (bm && lane > __ffs(bm) - 1) cnt = 0;
+      unsigned long long incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+      const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (MODE == 2 && total > cap) { if (lane == 0) { atomicOr(err, ERR_SLAB); counts[j] = total; } continue; }
+      // 4. the same again, writing
+      if (MODE != 0 && total)
+        replay_lanes<true>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, on && cnt > 0, pro, true, r, pos_entry, mo.first_a, mo.first_len,
+                           sc, err, hits, w + incl - cnt, wend);
+      if (MODE != 1 && lane == 0) counts[j] = total;
+      continue;
+    }
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int*>(slow_flag)) + 1, 1ull);   // statistics: chunks replayed sequentially
     bool stop = false;
     while (!stop && pos < data_len) {
       // FindBytesReuse(chunk[pos:data_len]): attempts at pos, f+1, ...

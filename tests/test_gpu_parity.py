@@ -369,3 +369,26 @@ def test_match_multi_one_launch_for_the_suite():
     # a sub-range of the program table (prog_first[0] > 0) gives the same flags
     sub = rg.match_multi(pats[10:20], data, offs, first[10:21])
     assert np.array_equal(sub, got[first[10]:first[20]])
+
+
+def test_find_all_kernel_edge_domains():
+    """Edge domains of the FindAll kernels, on the kernels themselves: cursor gaps of 2^22 bytes and more (the chain's
+    64-bit path and its float/integer quotient repair), filter hits that touch (the SWAR test's redo path), buffers of
+    exactly one, two and three chain parts (worklists of length 0 / 1), a walk longer than the event log."""
+    p, o = pair(synth.URL_PATTERN)
+    u = b"http://ab.cd/e"
+    # gaps >= 2^22 before a match, then short and long match lengths right behind each other
+    buf = bytearray(b"x" * ((1 << 22) + 4099)) + u + b" " + bytearray(b"y" * ((1 << 22) + 17)) + b"https://a.bc " + u * 3
+    check_find_all(p, o, bytes(buf))
+    check_find_all(p, o, b"q" * (9 << 20) + u)                     # one match behind a 9 MiB gap: 674 k repeats of it
+    # touching / overlapping prefix occurrences
+    for s in (b"hthttp://a.b", b"httphttp://a.b", b"http:/http://a.b/http://c.d", b"hhhhttp://x.yz httpp://q.r http//:", b"http://" * 300):
+        check_find_all(p, o, s)
+        check_find_all(p, o, s * 700)
+    # part geometry: 128 KiB chain parts
+    base = synth.make_buffer("url", 3 * (128 << 10) + 64)
+    for n in ((128 << 10), (128 << 10) + 1, (256 << 10) - 1, (256 << 10), (256 << 10) + 30, 3 * (128 << 10)):
+        check_find_all(p, o, base[:n])
+    # a URL with more state changes than the event log holds: host labels and path segments alternate a hundred times
+    long_url = b"http://" + b".".join([b"a"] * 60) + b":8080/" + b"/".join([b"b"] * 60)
+    check_find_all(p, o, b"see " + long_url + b" and " + u)

@@ -96,3 +96,45 @@ def test_chunk_range_sharding_matches_whole():
     assert np.array_equal(np.concatenate([x[1] for x in parts]), so)
     assert np.array_equal(np.concatenate([x[2] for x in parts]), ci)
     assert np.array_equal(np.concatenate([x[3] for x in parts]), recs)
+
+
+def test_lane_parallel_chase_boundaries():
+    """The chase splits a chunk over the 32 lanes of a warp at sync points (kernels_stream.cuh, chase_range).  Put the
+    cases that couple ranges exactly where ranges meet (multiples of 2 KiB in a 64 KiB chunk, of 32 KiB in a 1 MiB one):
+    dates straddling them, skip-restart prefixes, a skipped copy of a date's text far before the real match (bytes.Index
+    then reports the copy, from another lane's range: the chunk must take the sequential replay), digit runs longer than
+    a range (no sync point there), and heavy digit noise."""
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    rng = np.random.default_rng(11)
+    for bufsize, step in ((0, 2048), (1 << 20, 32768)):
+        n = 3 * (bufsize or 65536) + 777
+        buf = bytearray(rng.choice(np.frombuffer(b"abcdefgh \n", dtype=np.uint8), size=n).tobytes())
+        for edge in range(step, n - 64, step):
+            kind = (edge // step) % 6
+            if kind == 0:
+                buf[edge - 4:edge + 6] = b"2024-01-15"                  # straddles the nominal range start
+            elif kind == 1:
+                buf[edge - 3:edge + 8] = b"12024-02-16"                 # skip-restart prefix across it
+            elif kind == 2:
+                buf[edge - 300:edge + 300] = b"7" * 600                 # digits all over the sync window
+            elif kind == 3:
+                buf[edge + 250:edge + 260] = b"2031-12-31"              # right behind the cover window
+            elif kind == 4:
+                buf[edge - 1:edge + 10] = b"-2024-03-17"
+        check_reader(p, o, bytes(buf), bufsize)
+    # a skipped copy of the text, then the real match several ranges later and nothing in between
+    buf = bytearray(b"x" * 70000)
+    buf[100:111] = b"12024-01-15"
+    buf[9000:9010] = b"2024-01-15"
+    buf[30000:30010] = b"2024-01-15"
+    assert check_reader(p, o, bytes(buf)) >= 3
+    # digit run longer than several ranges, dates inside and after it
+    buf = bytearray(b"y" * 200000)
+    buf[3000:15000] = b"5" * 12000
+    buf[9000:9010] = b"2024-05-05"
+    buf[15003:15013] = b"2024-06-06"
+    check_reader(p, o, bytes(buf))
+    # heavy digit / dash noise
+    for noise in (0.2, 0.5):
+        check_reader(p, o, synth.make_buffer("stream", 2 * synth.BLOCK + 17, digit_noise=noise))
+        check_reader(p, o, synth.make_buffer("stream", 2 * synth.BLOCK + 17, digit_noise=noise), 1 << 20)
