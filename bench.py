@@ -346,10 +346,12 @@ class FindAllWork:
         self.n_bytes = int(gib * (1 << 30))
         self.blocks = (self.n_bytes + synth.BLOCK - 1) // synth.BLOCK
         t0 = time.perf_counter()
-        # N > 1: ONE logical buffer of world * n_bytes, rank r holds bytes [r*n_bytes, (r+1)*n_bytes) plus a
-        # halo (the next rank's first MiB, regenerated locally from the same block generator: no exchange)
+        # N > 1: ONE logical buffer of world * n_bytes, rank r holds bytes [r*n_bytes, (r+1)*n_bytes) plus a halo (the
+        # next rank's first MiB) and a pre-halo (the previous rank's last MiB), both regenerated locally from the same
+        # block generator: no exchange of input bytes
         self.halo = synth.BLOCK if (world > 1 and rank < world - 1) else 0
-        self.buf = synth.make_buffer(wl["kind"], self.n_bytes + self.halo, first_block=rank * self.blocks, device=dev)
+        self.pre = synth.BLOCK if (world > 1 and rank > 0) else 0
+        self.buf = synth.make_buffer(wl["kind"], self.pre + self.n_bytes + self.halo, first_block=rank * self.blocks - (1 if self.pre else 0), device=dev)
         torch.cuda.synchronize()
         self.gen_s = time.perf_counter() - t0
         self.nc = self.pat.num_cap
@@ -359,7 +361,8 @@ class FindAllWork:
         self.n_rec = C.c_uint64()
         self.exit_cur = C.c_int64()
         self.shard_start = rank * self.n_bytes
-        self.gather_i64 = rdist.torch_all_gather_i64(device=dev) if world > 1 else None
+        self.gather_pair = rdist.torch_all_gather_pair(device=dev) if world > 1 else None
+        self.redos = 0
         self.exchange_rounds = 0
         self.entry_global = 0
         self.phase = (C.c_float * 4)()
@@ -381,40 +384,46 @@ class FindAllWork:
             self.step_phase = [self.phase[0], self.phase[1], self.phase[2]]
             self.total_matches = r
             return r
-        # sharded: scan once, then replay the cursor until every rank's entry == its predecessor's exit
-        calls = [0]
-
-        def shard_call(entry_global, mode):
-            r = L.rgx_find_all_shard_dev(ctx, pat._h, self.buf.data_ptr(), self.n_bytes + self.halo, self.n_bytes, int(rank == world - 1),
-                                         entry_global - self.shard_start, self.shard_start, mode, self.d_out.data_ptr(),
-                                         self.d_reps.data_ptr(), self.cap_rec, C.byref(self.n_rec), C.byref(self.exit_cur))
-            self._lib.check(r)
-            return r
-        last_entry = [0]
-
-        def resolve(entry_global):
-            # mode bit 1: cursor replay only; bit 0: the scan of this step is already cached
-            shard_call(entry_global, 2 | int(calls[0] > 0))
-            L.rgx_ctx_last_timing(ctx, self.phase)
-            if calls[0] == 0:
-                self.step_phase[0], self.step_phase[1] = self.phase[0], self.phase[1]
-            else:
-                self.step_phase[1] += self.phase[1]      # a corrected replay
-            calls[0] += 1
-            last_entry[0] = entry_global
-            return self.shard_start + self.exit_cur.value, None
-
-        def finish():
-            r = shard_call(last_entry[0], 4)      # output only
-            L.rgx_ctx_last_timing(ctx, self.phase)
-            self.step_phase[2] = self.phase[2]
-            return r
-        entry, _, total_local, rounds = self.rdist.resolve_cursor_chain(resolve, rank, world, self.shard_start, self.gather_i64, finish=finish,
-                                                                          all_starts=[r * self.n_bytes for r in range(world)])
+        # sharded: every rank > 0 carries the cursor through its pre-halo, ONE 16-byte all-gather confirms entry == the
+        # predecessor's exit (a rank whose carried cursor was wrong redoes its shard from the right entry)
+        total_local, entry, rounds = self._sharded_pass(self.buf.data_ptr())
         self.exchange_rounds = rounds
         self.entry_global = entry
         self.total_matches = total_local
         return total_local
+
+    def _sharded_pass(self, buf_ptr):
+        L, ctx, pat, world, rank = self.L, self.ctx, self.pat, self.env["world"], self.env["rank"]
+        is_last = int(rank == world - 1)
+        entry_rel, exit_rel = C.c_int64(), C.c_int64()
+
+        def timing():
+            L.rgx_ctx_last_timing(ctx, self.phase)
+            self.step_phase = [self.phase[0], self.phase[1], self.phase[2]]
+
+        def run_pre():
+            if rank == 0:
+                r = L.rgx_find_all_shard_dev(ctx, pat._h, buf_ptr, self.n_bytes + self.halo, self.n_bytes, is_last, 0, 0, 0,
+                                             self.d_out.data_ptr(), self.d_reps.data_ptr(), self.cap_rec, C.byref(self.n_rec), C.byref(exit_rel))
+                self._lib.check(r)
+                timing()
+                return 0, exit_rel.value, r
+            r = L.rgx_find_all_shard_pre_dev(ctx, pat._h, buf_ptr, self.pre + self.n_bytes + self.halo, self.pre, self.n_bytes, is_last,
+                                             self.shard_start, self.d_out.data_ptr(), self.d_reps.data_ptr(), self.cap_rec,
+                                             C.byref(self.n_rec), C.byref(entry_rel), C.byref(exit_rel))
+            self._lib.check(r)
+            timing()
+            return self.shard_start + entry_rel.value, self.shard_start + exit_rel.value, r
+
+        def run_from(entry_global):
+            self.redos += 1
+            r = L.rgx_find_all_shard_dev(ctx, pat._h, buf_ptr + self.pre, self.n_bytes + self.halo, self.n_bytes, is_last,
+                                         entry_global - self.shard_start, self.shard_start, 0, self.d_out.data_ptr(), self.d_reps.data_ptr(),
+                                         self.cap_rec, C.byref(self.n_rec), C.byref(exit_rel))
+            self._lib.check(r)
+            return self.shard_start + exit_rel.value, r
+        entry, _, total_local, rounds = self.rdist.settle_pre_halo_chain(run_pre, run_from, rank, world, self.shard_start, self.gather_pair)
+        return total_local, entry, rounds
 
     def after_step(self):
         self.phases.append(tuple(self.step_phase))
@@ -423,7 +432,45 @@ class FindAllWork:
         n = int(self.n_rec.value)
         return [self.d_out[: n * self.nc], self.d_reps[:n]]
 
+    def e2e_sharded(self, k_e2e, barrier):
+        """N > 1: the SAME sharded computation from host buffers -- every step uploads the rank's part of the logical
+        buffer (shard + halos) from pinned memory, runs the sharded pass (with its cursor all-gather) and downloads the
+        rank's records."""
+        torch = self.torch
+        held = self.pre + self.n_bytes + self.halo
+        h_in = torch.empty(held, dtype=torch.uint8, pin_memory=True)
+        h_in.copy_(self.buf)
+        d_in = torch.empty(held + 16, dtype=torch.uint8, device=self.env["dev"])
+        n_rec_dev = int(self.n_rec.value)
+        cap_e2e = min(self.cap_rec, n_rec_dev + n_rec_dev // 8 + 65536)
+        h_out = torch.empty(cap_e2e * self.nc, dtype=torch.int64, pin_memory=True)
+        h_reps = torch.empty(cap_e2e, dtype=torch.int32, pin_memory=True)
+        stream = self.env["stream"]
+        torch.cuda.synchronize()
+        tot = [0]
+
+        def e2e_step():
+            with torch.cuda.stream(stream):
+                d_in[:held].copy_(h_in, non_blocking=True)
+            tot[0], _, _ = self._sharded_pass(d_in.data_ptr())
+            n = int(self.n_rec.value)
+            with torch.cuda.stream(stream):
+                h_out[: n * self.nc].copy_(self.d_out[: n * self.nc], non_blocking=True)
+                h_reps[:n].copy_(self.d_reps[:n], non_blocking=True)
+            stream.synchronize()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / k_e2e
+        assert tot[0] == self.total_matches and int(self.n_rec.value) == n_rec_dev
+        return dt, held, n_rec_dev * (self.nc * 8 + 4) + 16, "rgx_find_all_shard_pre_dev on the rank's part of the logical buffer; pinned H2D / D2H copies and the cursor all-gather inside the step"
+
     def e2e(self, k_e2e, barrier):
+        if self.env["world"] > 1:
+            return self.e2e_sharded(k_e2e, barrier)
         torch, L = self.torch, self.L
         h_in = torch.empty(self.n_bytes, dtype=torch.uint8, pin_memory=True)
         h_in.copy_(self.buf[:self.n_bytes])
@@ -483,8 +530,8 @@ class FindAllWork:
         world = self.env["world"]
         return {"bytes_per_gpu": self.n_bytes, "matches_per_step": int(self.total_matches), "distinct_records_per_step": int(self.n_rec.value),
                 "result_form": "run-length offset records left in HBM", "gen_seconds": self.gen_s,
-                "sharding": None if world == 1 else f"one logical buffer of {world}x{self.n_bytes} B, 1 MiB halo, exit-cursor all_gather (NCCL), "
-                            f"{self.exchange_rounds} exchange round(s); e2e is per-rank host buffers"}
+                "sharding": None if world == 1 else f"one logical buffer of {world}x{self.n_bytes} B, 1 MiB halo + 1 MiB pre-halo per rank, one "
+                            f"16-byte all_gather (NCCL) per step confirms the carried cursors: {self.exchange_rounds} round(s), {self.redos} redo(s) on rank 0"}
 
     def units(self):
         return self.n_bytes

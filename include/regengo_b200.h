@@ -190,6 +190,16 @@ int64_t rgx_find_all_shard_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* 
                                int32_t reuse_scan, int64_t* d_out_offsets, uint32_t* d_reps,
                                uint64_t cap_records, uint64_t* n_records, int64_t* exit_cursor);
 
+/* The same with a PRE-HALO: d_buf starts pre_len bytes (a multiple of 128 KiB; d_buf 16-byte aligned) before the
+ * shard.  The cursor is replayed through those bytes from a guess and nothing of them is reported; cursors entering the
+ * same records merge within a few of them, so *entry_at_shard (shard-relative) is the true entry cursor unless the
+ * pre-halo holds too few matches -- the caller checks it against the predecessor's exit cursor (one 16-byte all-gather
+ * per step) and, if it ever differs, redoes that shard with rgx_find_all_shard_dev and the right entry. */
+int64_t rgx_find_all_shard_pre_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_buf, uint64_t buf_len,
+                                   uint64_t pre_len, uint64_t shard_len, int32_t is_last, int64_t out_base,
+                                   int64_t* d_out_offsets, uint32_t* d_reps, uint64_t cap_records, uint64_t* n_records,
+                                   int64_t* entry_at_shard, int64_t* exit_cursor);
+
 /* ---- FindReader: func (T) FindReader(r io.Reader, cfg stream.Config, onMatch ...) error
  *      (streaming.go:85-255) for a reader that fills every Read (bytes.Reader semantics) over
  *      `stream[0:len]`.  buffer_size/max_leftover are stream.Config{BufferSize, MaxLeftover}

@@ -56,6 +56,8 @@ _SIGS = {
     "rgx_find_all_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rgx_find_all_shard_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P,
                                            C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64)]),
+    "rgx_find_all_shard_pre_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, _P, _P,
+                                               C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rgx_find_reader": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_uint64]),
     "rgx_find_reader_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                         _P, _P, _P, C.c_uint64]),

@@ -17,19 +17,21 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) findall_emit3_kernel(
     const FindAllBufs fb, const uint32_t* __restrict__ seg_sel, const unsigned long long* __restrict__ seg_reps,
     const unsigned long long* __restrict__ sel_base, const unsigned long long* __restrict__ reps_base,
     const unsigned long long* __restrict__ totals, const long long n_limit, int64_t* __restrict__ out,
-    uint32_t* __restrict__ out_reps, const uint64_t cap_records, unsigned long long* n_written) {
+    uint32_t* __restrict__ out_reps, const uint64_t cap_records, unsigned long long* n_written, const uint64_t skip_seg) {
   extern __shared__ __align__(16) long long stage_all[];   // [EMIT_WARPS][32 * nc]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint64_t seg = (uint64_t)blockIdx.x * EMIT_WARPS + warp;
+  // segments before skip_seg (a whole number of parts: the pre-halo of a shard) report nothing, and what they kept is
+  // taken off every output position
+  const uint64_t seg = skip_seg + (uint64_t)blockIdx.x * EMIT_WARPS + warp;
   const int nc = ENGINE == FIND_TDFA ? m.t_ntags : m.num_cap;
   long long* stage = stage_all + (size_t)warp * 32 * nc;
-  if (seg == 0 && lane == 0 && (n_limit < 0 || totals[1] <= (unsigned long long)n_limit)) *n_written = totals[0];
+  if (seg == skip_seg && lane == 0 && (n_limit < 0 || totals[1] <= (unsigned long long)n_limit)) *n_written = totals[0];
   if (seg >= n_seg) return;
   const uint32_t c = fb.count[seg];
   if (c == 0) return;
   const uint64_t p = seg / G;
-  unsigned long long o = sel_base[p] + seg_sel[seg];
-  unsigned long long cum = reps_base[p] + seg_reps[seg];
+  unsigned long long o = sel_base[p] + seg_sel[seg] - (skip_seg ? sel_base[skip_seg / G] : 0ull);
+  unsigned long long cum = reps_base[p] + seg_reps[seg] - (skip_seg ? reps_base[skip_seg / G] : 0ull);
   if (n_limit >= 0 && cum >= (unsigned long long)n_limit) return;
   const long long seg_pos = (long long)(seg * seg_bytes) - (long long)mis;
   for (uint32_t r0 = 0; r0 < c; r0 += 32) {

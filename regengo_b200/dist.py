@@ -115,6 +115,53 @@ def resolve_cursor_chain(resolve, rank, world, shard_start, all_gather_i64, firs
             raise RuntimeError("cursor exchange did not converge")
 
 
+def settle_pre_halo_chain(run_pre, run_from, rank, world, shard_start, all_gather_pair):
+    """FindAll over one buffer with PRE-HALOS: every rank > 0 replays the cursor through the last stretch of its
+    predecessor's shard (from a guess) before its own, so the cursor it carries into its shard is almost surely the true
+    one and ONE all-gather per step only has to confirm it.
+
+    run_pre() -> (entry_global, exit_global, payload): scan + replay + output with the pre-halo (rank 0: from cursor 0).
+    run_from(entry_global) -> (exit_global, payload): the same from an explicit entry cursor (the redo of a rank whose
+    carried cursor was wrong; its new exit is re-checked against its successor).
+    all_gather_pair((a, b)) -> list of every rank's (a, b); every rank calls it the same number of times.
+    Returns (entry_global, exit_global, payload, rounds)."""
+    entry, exit_cur, payload = run_pre()
+    rounds = 0
+    while True:
+        rounds += 1
+        pairs = all_gather_pair((entry, exit_cur))
+        want = [0] + [int(pairs[r - 1][1]) for r in range(1, world)]
+        bad = [r for r in range(world) if int(pairs[r][0]) != want[r]]
+        if not bad:
+            return entry, exit_cur, payload, rounds
+        if rank in bad:
+            entry = want[rank]
+            exit_cur, payload = run_from(entry)
+        if rounds > world + 1:
+            raise RuntimeError("cursor exchange did not converge")
+
+
+def torch_all_gather_pair(group=None, device=None):
+    """all_gather of two int64 per rank (NCCL on GPUs, gloo on CPU): one collective, one device-to-host read."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    src = torch.zeros(2, dtype=torch.int64, device=device)
+    dst = torch.zeros(2 * world, dtype=torch.int64, device=device)
+
+    def fn(pair):
+        src.copy_(torch.tensor([int(pair[0]), int(pair[1])], dtype=torch.int64), non_blocking=False)
+        if hasattr(dist, "all_gather_into_tensor") and (device is not None and str(device).startswith("cuda")):
+            dist.all_gather_into_tensor(dst, src, group=group)
+            flat = dst.tolist()
+        else:
+            out = [torch.zeros_like(src) for _ in range(world)]
+            dist.all_gather(out, src, group=group)
+            flat = [int(v) for t in out for v in t.tolist()]
+        return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
+    return fn
+
+
 def torch_all_gather_i64(group=None, device=None):
     """all_gather of one int64 per rank with torch.distributed (NCCL on GPUs, gloo on CPU): one collective
     into a preallocated tensor, one device-to-host read."""

@@ -148,3 +148,63 @@ def test_shard_buffer_geometry():
             assert sh.buf_len >= sh.shard_len and sh.start + sh.buf_len <= total
             assert sh.is_last == (sh.start + sh.buf_len == total)
         assert cover == total
+
+
+def _worker_pre(rank, world, port, total_len, pre, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        o = Oracle(compile_blob(synth.URL_PATTERN))
+        buf = synth.make_buffer("url", total_len)
+        sh = rd.shard_buffer(total_len, world, rank, halo=4096, align=4096)
+        recs = _records_for_shard(o, buf, sh)
+        # the pre-halo: the records of the last `pre` bytes of the predecessor's shard
+        pre_start = max(0, sh.start - pre)
+        pre_sh = rd.Shard(rank, world, pre_start, sh.start - pre_start, sh.start + 4096 - pre_start, False)
+        pre_recs = _records_for_shard(o, buf, pre_sh) if rank > 0 else []
+        redone = [0]
+
+        def run_pre():
+            if rank == 0:
+                ex, out = _replay_tdfa(recs, 0, total_len)
+                return 0, ex, out
+            carried, _ = _replay_tdfa(pre_recs, pre_start, total_len)      # guess: the cursor stands at the pre-halo's first byte
+            ex, out = _replay_tdfa(recs, carried, total_len)
+            return carried, ex, out
+
+        def run_from(entry):
+            redone[0] += 1
+            return _replay_tdfa(recs, entry, total_len)
+        entry, exit_cur, payload, rounds = rd.settle_pre_halo_chain(run_pre, run_from, rank, world, sh.start, rd.torch_all_gather_pair())
+        q.put((rank, entry, exit_cur, sum(k for _, _, k in payload), rounds, redone[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,pre", [(2, 65536), (3, 65536), (3, 300), (3, 10 ** 9)])
+def test_pre_halo_cursor_confirmation_gloo(world, pre):
+    """The pre-halo protocol of the sharded FindAll (dist.settle_pre_halo_chain): a rank carries the cursor through a
+    pre-halo from a guess; cursors merge after some records, so a long pre-halo (the bench uses 1 MiB, about 3500
+    records) makes the carried cursor the true one and one gather confirms it.  Short ones (64 KiB, 300 bytes) may
+    fail the check: the ranks then redo from the right entry -- the result is the sequential one either way.  A
+    pre-halo reaching back to byte 0 starts from the true cursor and is always confirmed at once."""
+    total_len = 6 * 65536 + 123
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_pre, args=(r, world, port, total_len, pre, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = Oracle(compile_blob(synth.URL_PATTERN))
+    n, _ = o.find_all(synth.make_buffer("url", total_len))
+    assert sum(r[3] for r in res) == n
+    assert res[0][1] == 0
+    for r in range(1, world):
+        assert res[r][1] == res[r - 1][2]          # every entry is the predecessor's exit
+    if pre >= total_len:
+        assert all(r[5] == 0 for r in res) and all(r[4] == 1 for r in res)   # confirmed at once: no redo, one round
