@@ -204,7 +204,8 @@ int64_t rgx_find_all_shard_pre_dev(rgx_ctx* c, const rgx_program* p, const uint8
  *      (streaming.go:85-255) for a reader that fills every Read (bytes.Reader semantics) over
  *      `stream[0:len]`.  buffer_size/max_leftover are stream.Config{BufferSize, MaxLeftover}
  *      before ApplyDefaults (0 => defaults).  Per match: StreamOffset, ChunkIndex and the offset
- *      record relative to the chunk buffer.  The callback's early stop is applied by the caller
+ *      record in ABSOLUTE STREAM OFFSETS (the reference's slices alias its chunk buffer; a shim
+ *      rebuilds them as stream[s:e] or subtracts the chunk's stream offset).  Early stop is the caller's
  *      (truncate at the first `false`).  Returns the match count (see rgx_find_all for cap).
  *      first_chunk/n_chunks select a chunk range [first_chunk, first_chunk+n_chunks) so that a
  *      stream can be sharded over GPUs (n_chunks < 0: to the end).                              */

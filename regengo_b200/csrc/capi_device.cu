@@ -317,6 +317,8 @@ static int match_multi_dev(rgx_ctx* c, const rgx_program* const* progs, uint32_t
 
 extern "C" {
 
+void rgx_ctx_destroy(rgx_ctx* c);
+
 int rgx_ctx_create(int32_t device, rgx_ctx** out) {
   if (!out) { set_error("rgx_ctx_create: null argument"); return RGX_EINVAL; }
   int n = 0;
@@ -337,13 +339,16 @@ int rgx_ctx_create(int32_t device, rgx_ctx** out) {
     set_error("regengo_b200 is built for sm_100a only");
     return RGX_ECUDA;
   }
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-  CU(cudaMallocHost(&c->h_small, 4096));
+  // (a half-built context is torn down by rgx_ctx_destroy: it frees whatever exists so far)
+  auto fail = [&](cudaError_t e, const char* what) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); rgx_ctx_destroy(c); return RGX_ECUDA; };
+  cudaError_t e2;
+  if ((e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
+  if ((e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
+  if ((e2 = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e2, "cudaStreamCreate");
+  if ((e2 = cudaMallocHost(&c->h_small, 4096)) != cudaSuccess) return fail(e2, "cudaMallocHost");
   int rc = ensure(c, c->small, 4096);
-  if (rc) { delete c; return rc; }
-  CU(cudaMemsetAsync(c->small.p, 0, 4096, c->stream));
+  if (rc) { rgx_ctx_destroy(c); return rc; }
+  if ((e2 = cudaMemsetAsync(c->small.p, 0, 4096, c->stream)) != cudaSuccess) return fail(e2, "cudaMemsetAsync");
   *out = c;
   return RGX_OK;
 }

@@ -118,6 +118,17 @@ static void negate_class(std::vector<int32_t>& r) {
   r.swap(out);
 }
 
+#include "unicode_tables.inc"
+
+// parse.go: unicodeTable.  "Any", then unicode.Categories[name], then unicode.Scripts[name] (exact, case-sensitive names).
+static bool unicode_table(const std::string& name, std::vector<int32_t>& pairs) {
+  pairs.clear();
+  if (name == "Any") { pairs = {0, MaxRune}; return true; }
+  for (const UniTable& t : kUniTables)
+    if (name == t.name) { pairs.assign(t.pairs, t.pairs + 2 * (size_t)t.n_pairs); return true; }
+  return false;
+}
+
 static const std::vector<int32_t> kPerlD = {'0', '9'};
 static const std::vector<int32_t> kPerlS = {'\t', '\n', '\f', '\r', ' ', ' '};
 static const std::vector<int32_t> kPerlW = {'0', '9', 'A', 'Z', '_', '_', 'a', 'z'};
@@ -734,6 +745,35 @@ struct Parser {
     return true;
   }
 
+  // parse.go: (*parser).parseUnicodeClass.  pos at '\\'; returns true if it consumed \pN, \p{Name}, \P.. (err set on a
+  // bad name: once the escape is seen the parser is committed).  Folded classes ((?i)) never get here: FoldCase is rejected.
+  bool parse_unicode_class(const std::string& s, size_t& pos, std::vector<int32_t>& cls) {
+    if (!(flags & UnicodeGroups) || s.size() - pos < 2 || s[pos] != '\\' || (s[pos + 1] != 'p' && s[pos + 1] != 'P')) return false;
+    int sign = s[pos + 1] == 'P' ? -1 : +1;
+    size_t t = pos + 2;
+    if (t >= s.size()) { err = "invalid character class range"; return true; }
+    std::string name;
+    if (s[t] != '{') {
+      // single-letter name (one rune)
+      int32_t c;
+      size_t t2 = t;
+      if (!next_rune(s, t2, c, err)) return true;
+      name = s.substr(t, t2 - t);
+      t = t2;
+    } else {
+      const size_t end = s.find('}', pos);
+      if (end == std::string::npos) { err = "invalid character class range"; return true; }
+      name = s.substr(pos + 3, end - (pos + 3));
+      t = end + 1;
+    }
+    if (!name.empty() && name[0] == '^') { sign = -sign; name = name.substr(1); }
+    std::vector<int32_t> tab;
+    if (!unicode_table(name, tab)) { err = "invalid character class range"; return true; }
+    if (sign > 0) append_class(cls, tab); else append_negated_class(cls, tab);
+    pos = t;
+    return true;
+  }
+
   // parse.go: (*parser).parseClass.  pos points at '['.
   bool parse_class(const std::string& s, size_t& pos) {
     size_t t = pos + 1;
@@ -768,9 +808,7 @@ struct Parser {
           continue;
         }
       }
-      if (s.size() - t >= 2 && s[t] == '\\' && (s[t + 1] == 'p' || s[t + 1] == 'P')) {
-        err = "unsupported: Unicode class \\p{..}"; return false;
-      }
+      if (parse_unicode_class(s, t, cls)) { if (!err.empty()) return false; continue; }
       if (parse_perl_class_escape(s, t, cls)) continue;
       int32_t lo, hi;
       if (!parse_class_char(s, t, lo)) return false;
@@ -919,11 +957,16 @@ struct Parser {
             }
           }
           if (handled) break;
-          if (s.size() - t >= 2 && (s[t + 1] == 'p' || s[t + 1] == 'P')) {
-            err = "unsupported: Unicode class \\p{..}"; return nullptr;
-          }
           Regexp* re = new_regexp(OpCharClass);
           re->flags = flags;
+          if (s.size() - t >= 2 && (s[t + 1] == 'p' || s[t + 1] == 'P')) {
+            // parse.go: the escape site of parseUnicodeClass
+            if (parse_unicode_class(s, t, re->rune)) {
+              if (!err.empty()) return nullptr;
+              push(re);
+              break;
+            }
+          }
           if (parse_perl_class_escape(s, t, re->rune)) { push(re); break; }
           int32_t c;
           if (!parse_escape(s, t, c)) return nullptr;
