@@ -227,16 +227,21 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
         }
       }
       const size_t ndesc = desc.size();
-      const size_t bytes = (rows.size() + desc.size() + fent.size() + 64) * 4;
+      const size_t bytes = (rows.size() + desc.size() * 8 + 64) * 4;
       if (fits && ndesc <= 1022 && (size_t)t.num_states * 1024 < (1u << 22) && bytes <= S6_IMAGE_LIMIT) {
         align4();
         m.w6_off = (uint32_t)w.size();
         w.insert(w.end(), rows.begin(), rows.end());
+        // descriptor table: 8 words per descriptor = {flags | n << 24, S6_FENT entries, padding}: one shift to address
+        align4();
         m.w6_desc = (uint32_t)w.size() - m.w6_off;
-        w.insert(w.end(), desc.begin(), desc.end());
+        for (size_t d = 0; d < ndesc; d++) {
+          w.push_back(desc[d]);
+          for (uint32_t q = 0; q < S6_FENT; q++) w.push_back(fent[d * S6_FENT + q]);
+          for (uint32_t q = 1 + S6_FENT; q < 8; q++) w.push_back(0);
+        }
         m.w6_ndesc = (int32_t)ndesc;
-        m.w6_fent = (uint32_t)w.size() - m.w6_off;
-        w.insert(w.end(), fent.begin(), fent.end());
+        m.w6_fent = m.w6_desc + 1;
         m.w6_init = (uint32_t)w.size() - m.w6_off;
         for (int x : t.init_tags_any) w.push_back((uint32_t)x);
         align4();

@@ -44,11 +44,12 @@ struct DevMeta {
   //          transition tag list fires and the step is either a self-loop or a move between two states that accept
   //          neither in the text nor at its end.  idx 0x3FF (S6_DEAD) = no transition (bytes >= 128 included,
   //          tdfa.go:944-946).  Any other idx = EVENT, described by desc[idx].
-  //   desc   1 word per descriptor: accepts:1 (S6_ACC) | accepts at EOT:1 (S6_ACC_EOT) | n:3 << 24 -- flags of the event's
-  //          next state and the number of tag entries
-  //   fent   S6_FENT words per descriptor, the event's tag actions in application order: tag * 128 | offset:8 << 16,
-  //          S6_ENT_ACCEPT set on the next state's accept actions (applied at the end of the state's run, and only
-  //          while that state accepts); the others are the transition's actions (applied at the step's position)
+  //   desc   8 words per descriptor (w6_fent = w6_desc + 1):
+  //          [0] accepts:1 (S6_ACC) | accepts at EOT:1 (S6_ACC_EOT) | n:3 << 24 -- flags of the event's next state and the
+  //              number of tag entries
+  //          [1..4] the event's tag actions in application order: tag * 128 | offset:8 << 16, S6_ENT_ACCEPT set on the next
+  //              state's accept actions (applied at the end of the state's run, and only while that state accepts); the
+  //              others are the transition's actions (applied at the step's position)
   //   init   tags set to the start position by initialTagsAny
   uint32_t w6_off, w6_words, w6_desc, w6_fent, w6_init;
   int32_t w6_ok, w6_ndesc;

@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
   uint32_t* Q = wbase + S6_SLOTS * S6_SLOTW;                               // S6_QCAP entries: j << 20 | range-relative start
   uint32_t* SV = Q + S6_QCAP;                                              // parked walker state: SV[i * 32 + lane]
   int32_t* T = reinterpret_cast<int32_t*>(SV) + lane;                      // tags of the replay (same words): T[j * 32]
-  const uint32_t desc_s = rows_s + m.w6_desc * 4u;
-  const uint32_t fent_s = rows_s + m.w6_fent * 4u;
-  const uint32_t tags_s = slots_s + (S6_SLOTS * S6_SLOTW + S6_QCAP) * 4u + lane * 4u;   // this lane's tag j is at tags_s + 128 j
+  uint32_t desc_s = rows_s + m.w6_desc * 4u;                               // descriptor d at desc_s + 32 d: flags, then its tag entries
+  uint32_t tags_s = slots_s + (S6_SLOTS * S6_SLOTW + S6_QCAP) * 4u + lane * 4u;   // this lane's tag j is at tags_s + 128 j
+  asm volatile("" : "+r"(desc_s), "+r"(tags_s));
   const uint32_t* initt = smem_all + m.w6_init;
   const uint32_t start_row = rows_s + (uint32_t)m.t_start_any * 1024u;
   const uint8_t* abuf = buf - mis;                        // 16-byte aligned view of the buffer
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
       uint32_t la = 0;
       uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, nl);
       for (uint32_t e = 0; e < nmax; e++)
-        if (e < nl && (lds32(desc_s + (lds32(ss + 8 + e * 4) >> 22) * 4u) & S6_ACC)) la = e + 1;
-      if (((hdr >> 30) & 1u) && nl && (lds32(desc_s + (lds32(ss + 8 + (nl - 1) * 4) >> 22) * 4u) & S6_ACC_EOT)) la = nl;
+        if (e < nl && (lds32(desc_s + (lds32(ss + 8 + e * 4) >> 22) * 32u) & S6_ACC)) la = e + 1;
+      if (((hdr >> 30) & 1u) && nl && (lds32(desc_s + (lds32(ss + 8 + (nl - 1) * 4) >> 22) * 32u) & S6_ACC_EOT)) la = nl;
       const bool matched = valid && la > 0;
       const int32_t match_end = !matched ? -1 : (la < nl ? (int32_t)((lds32(ss + 8 + la * 4) & 0x3FFFFFu) - st) : (int32_t)end_rel);
       for (int q = 0; q < nt; q++) T[q * 32] = -1;
@@ -149,11 +149,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
           const int32_t pos = (int32_t)((ev & 0x3FFFFFu) - st) + 1;
           int32_t run_end = (int32_t)end_rel;
           if (e + 1 < nl) { ev = lds32(ss + 12 + e * 4); run_end = (int32_t)((ev & 0x3FFFFFu) - st); }
-          const uint32_t d = lds32(desc_s + idx * 4u);
+          const uint32_t da = desc_s + idx * 32u;
+          const uint32_t d = lds32(da);
           const bool accp = (d & S6_ACC) || e + 1 == la;
           const uint32_t n = d >> 24;
           for (uint32_t i = 0; i < n; i++) {
-            const uint32_t en = lds32(fent_s + idx * (S6_FENT * 4u) + i * 4u);
+            const uint32_t en = lds32(da + 4u + i * 4u);
             const bool acc_ent = (en & S6_ENT_ACCEPT) != 0;
             if (!acc_ent || accp) sts32(tags_s + (en & 0xFFFFu), (uint32_t)((acc_ent ? run_end : pos) - (int32_t)((en >> 16) & 0xFFu)));
           }
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
           done_hi |= __reduce_or_sync(0xFFFFFFFFu, (fin_now && b >= 32) ? (1u << (b - 32)) : 0u);
         }
         // (the replay's tag words share the parking area: it is free while walks run)
+        if (done_lo == 0xFFFFFFFFu || tail) __syncwarp();   // the logs and headers other lanes wrote are read below
         while (done_lo == 0xFFFFFFFFu || (tail && fin_base < next_k)) {
           finalize(fin_base, min(32u, next_k - fin_base));
           fin_base += 32; done_lo = done_hi; done_hi = 0;

@@ -63,10 +63,10 @@ class Image:
     def entries(self, idx):
         """Tag entries of descriptor idx: [(tag, offset, is_accept_action)]."""
         d = self.plan
-        n = int(self.w[d["w6_desc"] + idx]) >> 24
+        n = int(self.w[d["w6_desc"] + 8 * idx]) >> 24
         out = []
         for i in range(n):
-            en = int(self.w[d["w6_fent"] + 4 * idx + i])
+            en = int(self.w[d["w6_fent"] + 8 * idx + i])
             assert (en & 0xFFFF) % 128 == 0
             out.append(((en & 0xFFFF) // 128, (en >> 16) & 0xFF, bool(en >> 31)))
         return out
@@ -90,7 +90,7 @@ class Image:
             ri += 1
         # the last event whose next state accepts
         for e, (idx, _) in enumerate(log):
-            dy = int(w[d["w6_desc"] + idx])
+            dy = int(w[d["w6_desc"] + 8 * idx])
             if dy & ACC or (e + 1 == len(log) and eob and dy & ACC_EOT):
                 lastacc = e + 1
         end_rel = ri - start
@@ -103,7 +103,7 @@ class Image:
             tags[int(w[d["w6_init"] + j])] = 0
         for e in range(lastacc):
             idx, pos = log[e]
-            dy = int(w[d["w6_desc"] + idx])
+            dy = int(w[d["w6_desc"] + 8 * idx])
             run_end = log[e + 1][1] if e + 1 < len(log) else end_rel
             accp = bool(dy & ACC) or e + 1 == lastacc
             for tg, off, is_acc in self.entries(idx):
