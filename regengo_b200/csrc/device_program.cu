@@ -183,7 +183,18 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     }
     // scan6 walk image (layout: device_program.cuh).  The walk distinguishes only two kinds of step: CHEAP ones,
     // whose whole effect is "go to that row", and EVENTS, which it logs and interprets when the walk is over.
-    if (m.prefix_len >= 1 && !nullable && t.start_begin == t.start_any && t.init_tags_begin == t.init_tags_any &&
+    // start filter of scan6: a literal first byte (prefix), or a first-byte SET of at most two ASCII ranges (\d, [a-z] ...)
+    int n_rng = 0;
+    uint8_t rlo[2] = {0, 0}, rhi[2] = {0, 0};
+    bool set_ok = m.prefix_len == 0;
+    for (uint32_t c = 0; set_ok && c < 128; c++) {
+      const bool in = (first.w[c >> 5] >> (c & 31)) & 1u;
+      const bool prev = c > 0 && ((first.w[(c - 1) >> 5] >> ((c - 1) & 31)) & 1u);
+      if (in && !prev) { if (n_rng == 2) { set_ok = false; break; } rlo[n_rng] = (uint8_t)c; rhi[n_rng] = (uint8_t)c; n_rng++; }
+      else if (in) rhi[n_rng - 1] = (uint8_t)c;
+    }
+    set_ok = set_ok && n_rng >= 1;
+    if ((m.prefix_len >= 1 || set_ok) && !nullable && t.start_begin == t.start_any && t.init_tags_begin == t.init_tags_any &&
         lists.size() <= 1023 && t.num_tags <= 16) {
       std::vector<uint32_t> rows((size_t)t.num_states * 256, S6_DEAD);
       std::map<std::pair<int, uint32_t>, uint32_t> desc_ids;
@@ -247,6 +258,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
         align4();
         m.w6_words = (uint32_t)w.size() - m.w6_off;
         m.w6_ok = 1;
+        if (m.prefix_len == 0) { m.w6_nrng = n_rng; for (int q = 0; q < 2; q++) { m.w6_rlo[q] = rlo[q]; m.w6_rhi[q] = rhi[q]; } }
       }
     }
   } else {

@@ -54,7 +54,10 @@ struct DevMeta {
   uint32_t w6_off, w6_words, w6_desc, w6_fent, w6_init;
   int32_t w6_ok, w6_ndesc;
   // (start filter of scan6: up to three of the first four bytes of the literal prefix -- necessary, not sufficient;
-  // the walk starts in startStateAny at the candidate start)
+  // the walk starts in startStateAny at the candidate start)  Without a literal first byte: the first-byte set as
+  // w6_nrng <= 2 ASCII ranges [w6_rlo, w6_rhi].
+  int32_t w6_nrng;
+  uint8_t w6_rlo[2], w6_rhi[2];
   int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
   uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;
   // FindAll candidate generator (start filter); see findall_kernels.cu

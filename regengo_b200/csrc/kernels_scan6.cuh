@@ -56,12 +56,13 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// PLEN: prefix bytes the filter looks at (1..4; of four it tests bytes 0, 1 and 3).  WARPS warps per CTA, GROUPS
+// PLEN: prefix bytes the filter looks at (1..4; of four it tests bytes 0, 1 and 3); 0: a first-byte set of one or two
+// ASCII ranges instead of a literal.  WARPS warps per CTA, GROUPS
 // window words per walk iteration.
-template <int PLEN, int WARPS, int MINB, int GROUPS>
+template <int PLEN, int WARPS, int MINB, int GROUPS, bool PF>
 __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
     const DevMeta m, const uint32_t* __restrict__ gimg, const uint8_t* __restrict__ buf, const uint64_t len,
-    const uint32_t mis, const uint64_t n_seg, const uint32_t R, const FindAllBufs fb, int* err) {
+    const uint32_t mis, const uint64_t n_seg, const uint32_t R, const uint32_t walk_at, const FindAllBufs fb, int* err) {
   extern __shared__ __align__(16) uint32_t smem_all[];
   __shared__ __align__(8) unsigned long long mbar;
   stage_image_tma(smem_all, gimg + m.w6_off, m.w6_words, &mbar);
@@ -96,6 +97,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
   const uint64_t load_end = (uint64_t)mis + len;          // bytes exist in [mis, load_end) (shard + halo)
   const uint32_t pv0 = (uint32_t)m.prefix_bytes[0] * 0x01010101u, pv1 = (uint32_t)m.prefix_bytes[1] * 0x01010101u;
   const uint32_t pv2 = (uint32_t)m.prefix_bytes[PLEN == 4 ? 3 : 2] * 0x01010101u;
+  // range filter (PLEN == 0): x + (0x80 - lo) has bit 7 iff x >= lo, x + (0x7F - hi) iff x > hi (x <= 0x7F)
+  const uint32_t ge0 = (0x80u - m.w6_rlo[0]) * 0x01010101u, gt0 = (0x7Fu - m.w6_rhi[0]) * 0x01010101u;
+  const uint32_t ge1 = (0x80u - m.w6_rlo[1]) * 0x01010101u, gt1 = (0x7Fu - m.w6_rhi[1]) * 0x01010101u;
+  const bool two_ranges = m.w6_nrng > 1;
   const uint64_t n_ranges = (n_seg + R - 1) / R;
   const uint64_t total_warps = (uint64_t)gridDim.x * WARPS;
 
@@ -299,6 +304,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
       uint32_t e0 = 0, e1 = 0;   // flags, bit 8*byte + word (word 0..7): 32 bytes each
       if (blk_a >= mis && blk_a + S6_BLK <= end_a && blk_a + S6_BLK + 4 <= load_end) {
         uint32_t w[17];
+        // the block after this one into L2 -> L1 while this one is filtered and walked (no registers held across
+        // the walk phase: a prefetch, not a load)
+        if (PF && blk_a + 2 * S6_BLK <= load_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + off + S6_BLK));
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const uint4 v = *reinterpret_cast<const uint4*>(sp + off + u * 16);
@@ -309,13 +317,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
         // touch; that (practically never) redoes the block with the exact test.
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          uint32_t z = w[q] ^ pv0;
-          if (PLEN > 1) z |= __funnelshift_r(w[q], w[q + 1], 8) ^ pv1;
-          if (PLEN > 2) z |= __funnelshift_r(w[q], w[q + 1], PLEN == 4 ? 24 : 16) ^ pv2;
-          const uint32_t d = (z - 0x01010101u) & ~z & 0x80808080u;
+          uint32_t d;
+          if (PLEN == 0) {
+            // first-byte SET: 0x80 in every byte of the word that lies in [lo, hi] (exact: no carries between bytes)
+            const uint32_t x = w[q] & 0x7F7F7F7Fu;
+            d = (x + ge0) & ~(x + gt0);
+            if (two_ranges) d |= (x + ge1) & ~(x + gt1);
+            d &= ~w[q] & 0x80808080u;
+          } else {
+            uint32_t z = w[q] ^ pv0;
+            if (PLEN > 1) z |= __funnelshift_r(w[q], w[q + 1], 8) ^ pv1;
+            if (PLEN > 2) z |= __funnelshift_r(w[q], w[q + 1], PLEN == 4 ? 24 : 16) ^ pv2;
+            d = (z - 0x01010101u) & ~z & 0x80808080u;
+          }
           if (q < 8) e0 |= d >> (7 - q); else e1 |= d >> (15 - q);
         }
-        if ((e0 & (e0 >> 8)) | (e1 & (e1 >> 8))) {
+        if (PLEN > 0 && ((e0 & (e0 >> 8)) | (e1 & (e1 >> 8)))) {
           e0 = 0; e1 = 0;
 #pragma unroll
           for (int q = 0; q < 16; q++) {
@@ -329,7 +346,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
       } else if (blk_a < end_a) {
         for (uint32_t i = 0; i < 64; i++) {
           const uint64_t ap = blk_a + (uint64_t)lane * 64 + i;
-          bool hit = ap >= mis && ap < end_a && abuf[ap] == m.prefix_bytes[0];
+          bool hit = ap >= mis && ap < end_a;
+          if (hit && PLEN == 0) { const uint32_t c = abuf[ap]; hit = (c >= m.w6_rlo[0] && c <= m.w6_rhi[0]) || (two_ranges && c >= m.w6_rlo[1] && c <= m.w6_rhi[1]); }
+          if (hit && PLEN > 0) hit = abuf[ap] == m.prefix_bytes[0];
           if (PLEN > 1) hit = hit && ap + 1 < load_end && abuf[ap + 1] == m.prefix_bytes[1];
           if (PLEN > 2) hit = hit && ap + (PLEN == 4 ? 3 : 2) < load_end && abuf[ap + (PLEN == 4 ? 3 : 2)] == m.prefix_bytes[PLEN == 4 ? 3 : 2];
           if (hit) { if (i < 32) e0 |= 1u << (8 * (i & 3) + (i >> 2)); else e1 |= 1u << (8 * (i & 3) + ((i - 32) >> 2)); }
@@ -392,7 +411,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
         __syncwarp();
       }
       const bool last = blk + 1 == n_blk;
-      if (last || q_tail - q_head >= 32) walk_run(last);
+      if (last || q_tail - q_head >= walk_at) walk_run(last);
     }
     if (lane == 0) {
       fb.count[seg0 + n_rseg - 1] = min(seg_count, fb.K);

@@ -51,7 +51,7 @@ def test_plan_invariants_over_the_corpus():
         d = p.device_plan()
         n += 1
         if d["fast_tdfa_scan"]:
-            assert d["find_engine"] == 2 and d["prefix_len"] >= 1 and d["nullable"] == 0
+            assert d["find_engine"] == 2 and (d["prefix_len"] >= 1 or d["gen_kind"] == 1) and d["nullable"] == 0
             assert 0 < d["scan6_image_bytes"] <= 96 * 1024 and 1 <= d["scan6_descriptors"] <= 1023
         if d["run_linear_elements"]:
             assert d["run_anchor"] == 1 and d["find_engine"] == 1

@@ -392,3 +392,35 @@ def test_find_all_kernel_edge_domains():
     # a URL with more state changes than the event log holds: host labels and path segments alternate a hundred times
     long_url = b"http://" + b".".join([b"a"] * 60) + b":8080/" + b"/".join([b"b"] * 60)
     check_find_all(p, o, b"see " + long_url + b" and " + u)
+
+
+def test_fast_scan_first_byte_set_filter():
+    """TDFA patterns without a literal first byte whose first-byte SET is one or two ASCII ranges (\\d..., [a-z]...) take
+    the fast scan with a SWAR range filter: every byte of the set is a candidate start.  Sparse and dense inputs, set
+    bytes at block / segment boundaries and at both ends, bytes >= 128 (never in an ASCII range)."""
+    semver = r"(?P<major>\d+)\.(?P<minor>\d+)\.(?P<patch>\d+)(?:-(?P<prerelease>[\w.-]+))?(?:\+(?P<build>[\w.-]+))?"
+    ipv4 = r"(?P<ip>(?P<a>\d{1,3})\.(?P<b>\d{1,3})\.(?P<c>\d{1,3})\.(?P<d>\d{1,3}))(?::(?P<port>\d{1,5}))?"
+    two = r"(?P<k>[a-cx-z][0-9]+)=(?P<v>\d+)"
+    rng = np.random.default_rng(3)
+    for pat, toks in ((semver, [b"1.2.3", b"10.20.30-rc.1+build.5", b"7.8", b"2024.1.15"]), (ipv4, [b"10.0.0.1", b"192.168.1.254:8080", b"1.2.3", b"999.1.1.1"]),
+                      (two, [b"a1=2", b"z99=100", b"d1=2", b"x5=", b"c0=7"])):
+        p, o = pair(pat, force_tdfa=True)
+        assert p.info.find_engine == 2 and p.device_plan()["fast_tdfa_scan"] == 1
+        words = [b"lorem", b"ipsum", b"v", b"caf\xc3\xa9", b"-", b"release", b"host", b"=", b"x", b"\n"]
+        parts = []
+        for _ in range(40000):
+            parts.append(toks[int(rng.integers(0, len(toks)))] if rng.integers(0, 12) == 0 else words[int(rng.integers(0, len(words)))])
+        buf = b" ".join(parts)
+        check_find_all(p, o, buf)
+        check_find_all(p, o, buf[7:70001])
+        for t in toks:
+            check_find_all(p, o, t)
+            check_find_all(p, o, (t + b" ") * 2500)            # dense: grows slabs or falls back to the generic scan
+            arr = bytearray(b"." * (2 * 32768 + 64))
+            for edge in (2048, 32768, 65536):
+                for d in range(-len(t), 2):
+                    if rng.integers(0, 2):
+                        arr[edge + d: edge + d + len(t)] = t
+            arr[:len(t)] = t
+            arr[len(arr) - len(t):] = t
+            check_find_all(p, o, bytes(arr))

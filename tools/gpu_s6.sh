@@ -17,8 +17,12 @@ except Exception as e:
     print("$name failed", e); print(open("$out/bench_c3_$name.err").read()[-2000:])
 PY
 }
-run G2 RGX_SCAN_GROUPS=2
-run G3 RGX_SCAN_GROUPS=3
+run G3PF0 RGX_SCAN_GROUPS=3 RGX_SCAN_PF=0
+run G3PF1 RGX_SCAN_GROUPS=3 RGX_SCAN_PF=1
+run G4PF1 RGX_SCAN_GROUPS=4 RGX_SCAN_PF=1
+run G3PF1W48 RGX_SCAN_GROUPS=3 RGX_SCAN_PF=1 RGX_SCAN_WALK_AT=48
+run G3PF1W64 RGX_SCAN_GROUPS=3 RGX_SCAN_PF=1 RGX_SCAN_WALK_AT=64
+run G3PF1W16 RGX_SCAN_GROUPS=3 RGX_SCAN_PF=1 RGX_SCAN_WALK_AT=16
 if [ "$2" != "noncu" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:findall_scan6 -s 3 -c 1 -o $out/scan6_c3 \
    python bench.py --workload c3 --gib 1 --steps 1 --warmup 3 --no-e2e --no-cpu --no-parity > $out/ncu_full_c3.log 2>&1
