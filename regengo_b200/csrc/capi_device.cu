@@ -585,7 +585,7 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   kv("parallel_findall", parallel_findall_ok(m, p->prog) ? 1 : 0);
   kv("scan6_image_bytes", (long long)m.w6_words * 4);
   kv("scan6_descriptors", m.w6_ndesc);
-  kv("w6_off", m.w6_off); kv("w6_desc", m.w6_desc); kv("w6_fent", m.w6_fent); kv("w6_init", m.w6_init);
+  kv("w6_off", m.w6_off); kv("w6_desc", m.w6_desc); kv("w6_fent", m.w6_fent); kv("w6_init", m.w6_init); kv("w6_maxev", m.w6_maxev);
   kv("tdfa_states", m.t_ns); kv("tdfa_tags", m.t_ntags); kv("tdfa_start_any", m.t_start_any); kv("tdfa_n_init_any", m.t_n_init_any);
   kv("run_anchor", m.run_ok);
   kv("run_literal", m.run_ok ? m.run_lit : -1);

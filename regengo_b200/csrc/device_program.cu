@@ -258,6 +258,30 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
         align4();
         m.w6_words = (uint32_t)w.size() - m.w6_off;
         m.w6_ok = 1;
+        // the most events one walk can log: longest path from the start state counting event edges (a cycle through
+        // an event edge: no bound).  The scan picks its per-candidate log size from it.
+        {
+          std::vector<int> dist((size_t)t.num_states, -1);
+          dist[t.start_any] = 0;
+          bool changed = true;
+          int rounds = 0;
+          while (changed && rounds <= t.num_states + 1) {
+            changed = false;
+            rounds++;
+            for (int st = 0; st < t.num_states; st++) {
+              if (dist[st] < 0) continue;
+              for (int c = 0; c < 128; c++) {
+                const uint32_t cell = rows[(size_t)st * 256 + c];
+                if (cell >= S6_DEAD) continue;
+                const int nx = (int)((cell & 0x3FFFFFu) / 1024u), wgt = cell >= S6_EVMIN ? 1 : 0;
+                if (dist[st] + wgt > dist[nx]) { dist[nx] = dist[st] + wgt; changed = true; }
+              }
+            }
+          }
+          int mx = 0;
+          for (int d : dist) mx = std::max(mx, d);
+          m.w6_maxev = changed ? 255 : std::min(mx, 255);
+        }
         if (m.prefix_len == 0) { m.w6_nrng = n_rng; for (int q = 0; q < 2; q++) { m.w6_rlo[q] = rlo[q]; m.w6_rhi[q] = rhi[q]; } }
       }
     }

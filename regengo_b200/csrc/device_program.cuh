@@ -57,6 +57,7 @@ struct DevMeta {
   // the walk starts in startStateAny at the candidate start)  Without a literal first byte: the first-byte set as
   // w6_nrng <= 2 ASCII ranges [w6_rlo, w6_rhi].
   int32_t w6_nrng;
+  int32_t w6_maxev;   // most events one walk can log (255: unbounded): sizes the per-candidate log of scan6
   uint8_t w6_rlo[2], w6_rhi[2];
   int32_t t_ns, t_ntags, t_start_begin, t_start_any, t_n_init_begin, t_n_init_any;
   uint32_t th_start_lo, th_start_hi, th_accept_lo, th_accept_hi, th_char_lo, th_char_hi;

@@ -266,6 +266,9 @@ template <int ENGINE>
 __global__ void __launch_bounds__(64) findall_chain4_kernel(const uint64_t n_seg, const uint32_t seg_bytes, const uint32_t G,
                                                             const uint64_t n_parts, const uint32_t mis, const uint64_t len_in,
                                                             const FindAllBufs fb, const Chain4Bufs cb, const int pass, int* err) {
+  // a failed scan (dense input, slab overflow, ...) left incomplete slabs behind: the host discards this attempt, and
+  // nothing downstream may follow positions read from entries that were never written
+  if (*(volatile int*)err) return;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t p;
   long long entry;

@@ -17,8 +17,10 @@ __global__ void __launch_bounds__(EMIT_WARPS * 32) findall_emit3_kernel(
     const FindAllBufs fb, const uint32_t* __restrict__ seg_sel, const unsigned long long* __restrict__ seg_reps,
     const unsigned long long* __restrict__ sel_base, const unsigned long long* __restrict__ reps_base,
     const unsigned long long* __restrict__ totals, const long long n_limit, int64_t* __restrict__ out,
-    uint32_t* __restrict__ out_reps, const uint64_t cap_records, unsigned long long* n_written, const uint64_t skip_seg) {
+    uint32_t* __restrict__ out_reps, const uint64_t cap_records, unsigned long long* n_written, const uint64_t skip_seg,
+    const int* err) {
   extern __shared__ __align__(16) long long stage_all[];   // [EMIT_WARPS][32 * nc]
+  if (*(const volatile int*)err) return;   // the attempt failed upstream (the host retries): the selections are not valid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // segments before skip_seg (a whole number of parts: the pre-halo of a shard) report nothing, and what they kept is
   // taken off every output position

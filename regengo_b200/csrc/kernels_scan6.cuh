@@ -35,16 +35,17 @@
 namespace rgx {
 
 constexpr int S6_SLOTS = 64;             // candidates in flight per warp (power of two)
-constexpr int S6_LOGCAP = 11;            // events per walk
-constexpr int S6_SLOTW = 2 + S6_LOGCAP;  // queue entry, end word, events (odd: consecutive slots fall into different banks)
+// LOGCAP (template parameter): events a walk may log, 11 or 15 (the count travels in 4 bits).  A slot is 2 + LOGCAP words:
+// queue entry, end word, events (odd: consecutive slots fall into different banks).  The host takes 11 when no walk of
+// the pattern can log more (DevMeta::w6_maxev, the longest event path of the automaton), else 15.
 constexpr uint32_t S6_QCAP = 128;        // queued candidates per warp (power of two)
 constexpr uint32_t S6_BLK = 2048;        // bytes per filter block (64 per lane)
 constexpr uint32_t S6_MAXR = 32;         // segments per range (queue entries hold a 20-bit range-relative start)
 constexpr uint32_t S6_MAXJ = 4096;       // slab entries per segment the queue entry can number
 constexpr int S6_SAVE = 8;               // parked walker state, words per lane
 
-__host__ __device__ inline size_t scan6_warp_words(int ntags) {
-  return (size_t)S6_SLOTS * S6_SLOTW + S6_QCAP + (size_t)(ntags > S6_SAVE ? ntags : S6_SAVE) * 32;
+__host__ __device__ inline size_t scan6_warp_words(int ntags, int logcap) {
+  return (size_t)S6_SLOTS * (2 + logcap) + S6_QCAP + (size_t)(ntags > S6_SAVE ? ntags : S6_SAVE) * 32;
 }
 
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -59,10 +60,11 @@ __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
 // PLEN: prefix bytes the filter looks at (1..4; of four it tests bytes 0, 1 and 3); 0: a first-byte set of one or two
 // ASCII ranges instead of a literal.  WARPS warps per CTA, GROUPS
 // window words per walk iteration.
-template <int PLEN, int WARPS, int MINB, int GROUPS, bool PF>
+template <int PLEN, int WARPS, int MINB, int GROUPS, bool PF, int LOGCAP>
 __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
     const DevMeta m, const uint32_t* __restrict__ gimg, const uint8_t* __restrict__ buf, const uint64_t len,
     const uint32_t mis, const uint64_t n_seg, const uint32_t R, const uint32_t walk_at, const FindAllBufs fb, int* err) {
+  constexpr int S6_LOGCAP = LOGCAP, S6_SLOTW = 2 + LOGCAP;
   extern __shared__ __align__(16) uint32_t smem_all[];
   __shared__ __align__(8) unsigned long long mbar;
   stage_image_tma(smem_all, gimg + m.w6_off, m.w6_words, &mbar);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int nt = m.t_ntags;
-  uint32_t* wbase = smem_all + m.w6_words + (size_t)warp * scan6_warp_words(nt);
+  uint32_t* wbase = smem_all + m.w6_words + (size_t)warp * scan6_warp_words(nt, LOGCAP);
   uint32_t slots_s = smem_u32(wbase);                                     // S6_SLOTS x S6_SLOTW words
   asm volatile("" : "+r"(slots_s));
   uint32_t* Q = wbase + S6_SLOTS * S6_SLOTW;                               // S6_QCAP entries: j << 20 | range-relative start
@@ -132,8 +134,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) findall_scan6_kernel(
       const uint32_t qe = valid ? lds32(ss) : 0u;
       const uint32_t hdr = valid ? lds32(ss + 4) : 0u;
       const uint32_t st = qe & 0xFFFFFu, j = qe >> 20;
-      const uint32_t nl = (hdr >> 22) & 15u, end_rel = (hdr & 0x3FFFFFu) - st;
-      if (hdr >> 31) atomicOr(err, ERR_DENSE);       // log overflow or a walk of a MiB: the generic scan decides
+      // (log overflow or a walk of a MiB: the generic scan decides, and nothing of that log is read)
+      const uint32_t nl = (hdr >> 31) ? 0u : ((hdr >> 22) & 15u), end_rel = (hdr & 0x3FFFFFu) - st;
+      if (hdr >> 31) atomicOr(err, ERR_DENSE);
       // the last event whose next state accepts (acceptStatesEOT counts when the walk consumed the input's last byte)
       uint32_t la = 0;
       uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, nl);

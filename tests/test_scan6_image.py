@@ -133,6 +133,7 @@ def check_pattern(pattern, inputs, **kw):
                 assert ref is None, (pattern, data, start)
                 continue
             got, nlog = img.walk(data, start)
+            assert nlog <= img.plan["w6_maxev"], (pattern, data, start, nlog)   # the bound that sizes the kernel's log
             if ref is None:
                 assert got is None, (pattern, data, start)
             else:
@@ -149,6 +150,17 @@ def test_url_pattern_log_interpretation():
     inputs = [b"see " + u + b"and " + u for u in urls[:150]] + [u.rstrip() for u in urls[150:]]   # also URLs cut by the end of the input
     inputs += [b"http://a.b:80/x", b"https://", b"http://a", b"http://a.b:/x", b"http://a.b:8", b"http://\xc3\xa9.com", b"httphttp://x.y/http://z"]
     assert check_pattern(synth.URL_PATTERN, inputs) > 400
+
+
+def test_first_byte_set_patterns_log_interpretation():
+    """Patterns without a literal first byte (the filter is a first-byte range test, every set byte is walked)."""
+    semver = r"(?P<major>\d+)\.(?P<minor>\d+)\.(?P<patch>\d+)(?:-(?P<prerelease>[\w.-]+))?(?:\+(?P<build>[\w.-]+))?"
+    ipv4 = r"(?P<ip>(?P<a>\d{1,3})\.(?P<b>\d{1,3})\.(?P<c>\d{1,3})\.(?P<d>\d{1,3}))(?::(?P<port>\d{1,5}))?"
+    assert check_pattern(semver, [b"v1.2.3 and 10.20.30-rc.1+build.5, 7.8 2024.1.15", b"1.2.3", b"1.2.", b"0.0.0-"], force_tdfa=True) > 40
+    assert check_pattern(ipv4, [b"10.0.0.1 192.168.1.254:8080 1.2.3 999.1.1.1:123456", b"1.1.1.1:", b"1234.1.1.1"], force_tdfa=True) > 40
+    img = Image(ipv4, force_tdfa=True)
+    assert img.plan["prefix_len"] == 0 and 11 < img.plan["w6_maxev"] <= 15      # takes the 15-event log
+    assert Image(synth.URL_PATTERN).plan["w6_maxev"] <= 11
 
 
 def test_corpus_tdfa_patterns_log_interpretation():

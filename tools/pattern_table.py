@@ -1,0 +1,139 @@
+#!/usr/bin/env python3
+"""Per-pattern FindAllBytes throughput of the device path over the reference's curated benchmark patterns
+(scripts/curated/cases.go:19-243): which scan kernel each one takes and what it reaches on a device-resident
+buffer.  One JSON line per pattern; CUDA-event phase times come from the library (rgx_ctx_last_timing).
+
+    python tools/pattern_table.py [--mib 512]
+
+Text: prose-like lowercase words with punctuation and newlines, one of the pattern's own sample tokens every
+~256 bytes (seeded).  Every pattern is first timed on 1 MiB; the large run is skipped when the probe says it
+would take longer than --budget-ms (memoised-backtracking patterns on long word runs)."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+EMAIL = [b"john.doe@example.com", b"a+b@c-d.io", b"support@mail.example.org"]
+URL = [b"http://example.com", b"https://api.example.com:8080/v1/users", b"https://cdn.example.org/a/b.js"]
+DATE = [b"2024-01-15", b"1999-12-31", b"2025-06-07"]
+CASES = [
+    ("Email", r"[\w\.+-]+@[\w\.-]+\.[\w\.-]+", EMAIL),
+    ("Greedy", r"(?:(?:a|b)|(?:k)+)*abcd", [b"abkkabcd", b"kkkabcd", b"ababab"]),
+    ("Lazy", r"(?:(?:a|b)|(?:k)+)+?abcd", [b"abkkabcd", b"kkkabcd", b"ababab"]),
+    ("EmailCapture", r"(?P<user>[\w\.+-]+)@(?P<domain>[\w\.-]+)\.(?P<tld>[\w\.-]+)", EMAIL),
+    ("URLCapture", r"(?P<protocol>https?)://(?P<host>[\w\.-]+)(?::(?P<port>\d+))?(?P<path>/[\w\./]*)?", URL),
+    ("DateCapture", r"(?P<year>\d{4})-(?P<month>\d{2})-(?P<day>\d{2})", DATE),
+    ("TDFAPathological", r"(?P<outer>(?P<inner>a+)+)b", [b"aaaab", b"aaaaaaaaaaaaaaaaaaaaac", b"ab"]),
+    ("TDFANestedWord", r"(?P<words>(?P<word>\w+\s*)+)end", [b"the end", b"foo bar baz end", b"ending"]),
+    ("TDFAComplexURL", r"(?P<scheme>https?)://(?P<auth>(?P<user>[\w.-]+)(?::(?P<pass>[\w.-]+))?@)?(?P<host>[\w.-]+)(?::(?P<port>\d+))?(?P<path>/[\w./-]*)?(?:\?(?P<query>[\w=&.-]+))?",
+     URL + [b"https://user:pw@host.example.com:8443/p/a-th?q=1&r=2"]),
+    ("TDFALogParser", r"(?P<timestamp>\d{4}-\d{2}-\d{2}T\d{2}:\d{2}:\d{2})(?:\.(?P<ms>\d{3}))?(?P<tz>Z|[+-]\d{2}:\d{2})?\s+\[(?P<level>\w+)\]\s+(?P<message>.+)",
+     [b"2024-01-15T10:30:00Z [INFO] started", b"2024-01-15T10:30:00.123+02:00 [ERROR] failed"]),
+    ("TDFASemVer", r"(?P<major>\d+)\.(?P<minor>\d+)\.(?P<patch>\d+)(?:-(?P<prerelease>[\w.-]+))?(?:\+(?P<build>[\w.-]+))?",
+     [b"1.2.3", b"10.20.30-rc.1+build.5", b"2.0.0-beta"]),
+    ("IPv4", r"(?P<ip>(?P<a>\d{1,3})\.(?P<b>\d{1,3})\.(?P<c>\d{1,3})\.(?P<d>\d{1,3}))(?::(?P<port>\d{1,5}))?",
+     [b"10.0.0.1", b"192.168.1.254:8080", b"1.2.3"]),
+    ("EmailSimple", r"(?P<user>\w+)@(?P<domain>\w+)\.(?P<tld>\w+)", [b"john@example.com", b"a@b.c"]),
+    ("Date", r"\d{4}-\d{2}-\d{2}", DATE),
+]
+WORDS = [b"the", b"quick", b"brown", b"fox", b"jumps", b"over", b"lazy", b"dog", b"and", b"then", b"has", b"happy", b"hour", b"with", b"a",
+         b"kind", b"banana", b"market", b"version", b"host", b"path", b"value", b"while", b"some", b"other", b"thing", b"is", b"in", b"of"]
+
+
+def make_block(tokens, n_bytes, seed):
+    rng = np.random.default_rng(seed)
+    out, size, since, sent = [], 0, 0, 0
+    while size < n_bytes:
+        if since >= 256:
+            t = tokens[int(rng.integers(0, len(tokens)))]
+            since = 0
+        else:
+            t = WORDS[int(rng.integers(0, len(WORDS)))]
+        sent += 1
+        sep = b".\n" if sent % 23 == 0 else b", " if sent % 7 == 0 else b" "
+        out.append(t + sep)
+        size += len(t) + len(sep)
+        since += len(t) + len(sep)
+    return np.frombuffer(b"".join(out)[:n_bytes], dtype=np.uint8)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mib", type=int, default=512)
+    ap.add_argument("--budget-ms", type=float, default=4000.0)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    import torch
+    import regengo_b200 as rg
+    from regengo_b200 import _lib
+    L = _lib.load()
+    dev = torch.device("cuda", 0)
+    ctx = rg.context(0)
+    _lib.check(L.rgx_ctx_enable_timing(ctx, 1))
+    n_bytes = args.mib << 20
+    block = 16 << 20
+    for name, pat, tokens in CASES:
+        if args.only and name not in args.only.split(","):
+            continue
+        p = rg.Pattern(pat)
+        plan = p.device_plan()
+        kernel = ("findall_scan6_kernel" if plan.get("fast_tdfa_scan") else "findall_scan_btrun_kernel" if plan.get("run_anchor") else "findall_scan_kernel")
+        host = make_block(tokens, block, seed=zlib.crc32(name.encode()) & 0xFFFF)
+        d_block = torch.from_numpy(host.copy()).to(dev)
+        buf = d_block.repeat((n_bytes + block - 1) // block)[:n_bytes].contiguous()
+        nc = p.num_cap
+        cap_rec = n_bytes // 16 + 1024
+        d_out = torch.empty(cap_rec * nc, dtype=torch.int64, device=dev)
+        d_reps = torch.empty(cap_rec, dtype=torch.int32, device=dev)
+        n_rec = C.c_uint64()
+        phase = (C.c_float * 4)()
+
+        def run(n):
+            r = L.rgx_find_all_dev(ctx, p._h, buf.data_ptr(), n, -1, d_out.data_ptr(), d_reps.data_ptr(), cap_rec, C.byref(n_rec))
+            _lib.check(r)
+            L.rgx_ctx_last_timing(ctx, phase)
+            return r, phase[0] + phase[1] + phase[2]
+
+        row = {"case": name, "find_engine": int(p.info.find_engine), "kernel": kernel, "num_cap": nc}
+        if p.info.find_engine == 0:
+            row["skipped"] = "no capture groups: the reference generates no Find* for it (regengo.go:110)"
+            print(json.dumps(row), flush=True)
+            continue
+        if p.info.find_memo:
+            # the reference clears its states x (len + 1) visited bitmap at every restart (find.go): quadratic in the
+            # buffer length on the CPU as well; parity for these runs at test sizes (tests/test_gpu_parity.py)
+            row["skipped"] = "memoised backtracking: quadratic in the buffer length in the reference itself"
+            print(json.dumps(row), flush=True)
+            continue
+        try:
+            run(1 << 20)
+            _, probe_ms = run(1 << 20)
+            row["probe_1mib_ms"] = round(probe_ms, 3)
+            if probe_ms * args.mib / 100.0 > args.budget_ms:
+                # the 1 MiB probe occupies about 1 % of the device's warps: the large run takes at least probe * MiB / 100
+                row["skipped"] = "probe says the large run exceeds the budget"
+            else:
+                run(n_bytes)
+                best = None
+                for _ in range(3):
+                    r, ms = run(n_bytes)
+                    if best is None or ms < best[1]:
+                        best = (r, ms, phase[0], phase[1], phase[2])
+                row.update(mib=args.mib, matches=int(best[0]), records=int(n_rec.value), ms=round(best[1], 3), scan_ms=round(best[2], 3),
+                           chain_ms=round(best[3], 3), emit_ms=round(best[4], 3), GBps=round(n_bytes / best[1] / 1e6, 1))
+        except Exception as e:  # noqa: BLE001
+            row["error"] = str(e)[:200]
+        print(json.dumps(row), flush=True)
+        del buf, d_out, d_reps, d_block
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
