@@ -200,6 +200,27 @@ int64_t rgx_find_all_shard_pre_dev(rgx_ctx* c, const rgx_program* p, const uint8
                                    int64_t* d_out_offsets, uint32_t* d_reps, uint64_t cap_records, uint64_t* n_records,
                                    int64_t* entry_at_shard, int64_t* exit_cursor);
 
+/* ---- ReplaceAllBytesAppend: func (T) ReplaceAllBytesAppend(input []byte, template string, buf []byte) []byte
+ *      (internal/compiler/replace.go:192-273; template syntax replace/template.go:60-163: $0 $1 $12 $name ${1}
+ *      ${name} $$).  Batch extension: input i is bytes[offs[i]:offs[i+1]]; its result is
+ *      out_bytes[out_offs[i]:out_offs[i+1]] (out_offs has n + 1 entries, results back to back).  *out_total = the
+ *      bytes all results take; if that exceeds out_cap nothing is written, out_offs is still filled and the call
+ *      returns RGX_ECAPACITY (call again with a buffer of *out_total bytes).  A malformed template -- the reference
+ *      panics -- returns RGX_EINVAL with the reference's message.  Per input the reference's loop runs literally:
+ *      FindBytesReuse on input[offset:], bytes.Index for the text, template expansion from that match's captures;
+ *      references to groups the pattern does not have expand to nothing.  Generated only for patterns with capture
+ *      groups (compiler.go:310-337), like Find*.                                                              */
+int rgx_replace_batch(rgx_ctx* c, const rgx_program* p, const char* tmpl, uint64_t tmpl_len, const uint8_t* bytes,
+                      const uint64_t* offs, uint64_t n, uint8_t* out_bytes, uint64_t out_cap, uint64_t* out_offs,
+                      uint64_t* out_total);
+int rgx_replace_batch_dev(rgx_ctx* c, const rgx_program* p, const char* tmpl, uint64_t tmpl_len, const uint8_t* d_bytes,
+                          const uint64_t* d_offs, uint64_t n, uint8_t* d_out_bytes, uint64_t out_cap,
+                          uint64_t* d_out_offs, uint64_t* out_total);
+/* replace.Parse + the lookups of the generated expansion, without running anything: RGX_OK or RGX_EINVAL.  The dump
+ * is a JSON list of resolved segments [[group or -1, "literal bytes in hex"], ...] (host only; returns its length). */
+int rgx_replace_template_check(const rgx_program* p, const char* tmpl, uint64_t tmpl_len);
+int64_t rgx_replace_template_dump(const rgx_program* p, const char* tmpl, uint64_t tmpl_len, char* buf, size_t cap);
+
 /* ---- FindReader: func (T) FindReader(r io.Reader, cfg stream.Config, onMatch ...) error
  *      (streaming.go:85-255) for a reader that fills every Read (bytes.Reader semantics) over
  *      `stream[0:len]`.  buffer_size/max_leftover are stream.Config{BufferSize, MaxLeftover}

@@ -46,6 +46,10 @@ def _load():
         L.orc_find_reader.argtypes = [P, P, C.c_int64, C.c_int64, C.c_int64, P, P, P, C.c_int64]
         L.orc_match_batch.argtypes = [P, P, P, C.c_uint64, P]
         L.orc_find_batch.argtypes = [P, P, P, C.c_uint64, P, P]
+        L.orc_replace_all.restype = C.c_int64
+        L.orc_replace_all.argtypes = [P, P, C.c_int64, P, C.c_int64, P, C.c_int64]
+        L.orc_replace_batch.restype = C.c_int64
+        L.orc_replace_batch.argtypes = [P, P, P, C.c_uint64, P, C.c_int64, P, C.c_int64, P]
         _lib = L
     return _lib
 
@@ -138,6 +142,32 @@ class Oracle:
         out = np.empty(n, dtype=np.uint8)
         _load().orc_match_batch(self._h, b.ctypes.data, o.ctypes.data, n, out.ctypes.data)
         return out
+
+    def replace_all(self, data, template):
+        """ReplaceAllBytes(input, template) -> bytes (ValueError on a malformed template: the reference panics)."""
+        out, _ = self.replace_batch(_as_u8(data), np.array([0, len(data)], dtype=np.uint64), template)
+        return out.tobytes()
+
+    def replace_batch(self, bytes_arr, offs, template):
+        """ReplaceAllBytesAppend per input -> (out_bytes, out_offs[n + 1])."""
+        b = _as_u8(bytes_arr)
+        o = np.ascontiguousarray(offs, dtype=np.uint64)
+        t = np.frombuffer(template.encode("utf-8") if isinstance(template, str) else bytes(template), dtype=np.uint8)
+        n = o.size - 1
+        out_offs = np.zeros(n + 1, dtype=np.uint64)
+        cap = int(b.size) + 64 * max(n, 1)
+        for _ in range(2):
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            r = _load().orc_replace_batch(self._h, b.ctypes.data, o.ctypes.data, n, t.ctypes.data if t.size else None, t.size,
+                                          out.ctypes.data, cap, out_offs.ctypes.data)
+            if r == -7:
+                raise ValueError("regengo: invalid replace template")
+            if r < 0:
+                raise NotImplementedError(f"oracle: template not decided by this restatement ({r})")
+            if r <= cap:
+                break
+            cap = int(r)
+        return out[:r], out_offs
 
     def find_batch(self, bytes_arr, offs):
         b = _as_u8(bytes_arr)

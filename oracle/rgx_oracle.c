@@ -615,3 +615,137 @@ void orc_find_batch(orc_prog* P, const uint8_t* bytes, const uint64_t* offs, uin
     found[i] = (uint8_t)(r == 1);
   }
 }
+
+/* ---- ReplaceAllBytesAppend (internal/compiler/replace.go:192-273) ------------------------------------
+ * Template: replace.Parse (replace/template.go:60-163), restated bytewise as the Go code indexes its string.
+ * isNameStart / isNameContinue take rune(byte): a byte >= 0x80 is judged as the Latin-1 code point of that value
+ * (unicode.IsLetter over U+0080..U+00FF: AA, B5, BA, C0-D6, D8-F6, F8-FF; unicode.IsDigit: none).  Braced names
+ * are checked rune by rune in the reference; this restatement only decides ASCII content and reports -8 for a
+ * braced reference with a byte >= 0x80 (tests keep to what it decides).  Returns -7 on a malformed template.      */
+enum { SEG_LIT = -1 };
+typedef struct { int group; int64_t lit_off, lit_len; } orc_seg;   /* literal bytes are tmpl[lit_off : lit_off+lit_len] or "$" (lit_off = -1) */
+
+static int latin1_letter(unsigned c) {
+  return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == 0xAA || c == 0xB5 || c == 0xBA || (c >= 0xC0 && c <= 0xD6) ||
+         (c >= 0xD8 && c <= 0xF6) || (c >= 0xF8 && c <= 0xFF);
+}
+static int t_name_start(unsigned c) { return c == '_' || latin1_letter(c); }
+static int t_name_continue(unsigned c) { return c == '_' || latin1_letter(c) || (c >= '0' && c <= '9'); }
+
+/* group index of a capture name (the switch of replace.go:436-453: named groups i >= 1), -1 when no case fires */
+static int name_to_group(const orc_prog* P, const uint8_t* name, int64_t nl) {
+  const uint32_t* w = P->w;
+  const uint8_t* b = (const uint8_t*)(w + w[H_OFF_NAMES]);
+  const size_t nb = (size_t)w[H_NAMES_WORDS] * 4;
+  size_t pos = 0;
+  const int groups = P->num_cap / 2;
+  for (int g = 0; g < groups && pos < nb; g++) {
+    const size_t len = b[pos++];
+    if (g >= 1 && len > 0 && (int64_t)len == nl && memcmp(b + pos, name, len) == 0) return g;
+    pos += len;
+  }
+  return -1;
+}
+
+static int template_parse(const orc_prog* P, const uint8_t* t, int64_t n, orc_seg* segs, int max_segs) {
+  int ns = 0;
+  const int groups = P->num_cap / 2;
+#define ADD(g, o, l) do { if (ns >= max_segs) return -9; segs[ns].group = (g); segs[ns].lit_off = (o); segs[ns].lit_len = (l); ns++; } while (0)
+#define ADD_GROUP(idx) do { if ((idx) >= 0 && (idx) < groups) ADD((int)(idx), 0, 0); } while (0)   /* CaptureByIndex: default -> nil */
+  int64_t i = 0, literal_start = 0;
+  while (i < n) {
+    if (t[i] != '$') { i++; continue; }
+    if (i > literal_start) ADD(SEG_LIT, literal_start, i - literal_start);
+    if (i + 1 >= n) { ADD(SEG_LIT, -1, 1); i++; literal_start = i; continue; }
+    const unsigned next = t[i + 1];
+    if (next == '$') { ADD(SEG_LIT, -1, 1); i += 2; literal_start = i; }
+    else if (next == '{') {
+      int64_t close = -1;
+      for (int64_t k = i; k < n; k++) if (t[k] == '}') { close = k; break; }
+      if (close < 0) return -7;                                  /* unclosed ${ */
+      const uint8_t* content = t + i + 2;
+      const int64_t cl = close - (i + 2);
+      if (cl == 0) return -7;                                    /* empty ${} */
+      for (int64_t k = 0; k < cl; k++) if (content[k] >= 0x80) return -8;
+      if (content[0] >= '0' && content[0] <= '9') {
+        int64_t index = 0;
+        for (int64_t k = 0; k < cl; k++) {
+          if (content[k] < '0' || content[k] > '9') return -7;   /* mixed digits and non-digits */
+          if (index < (1 << 24)) index = index * 10 + (content[k] - '0');
+        }
+        ADD_GROUP(index);
+      } else {
+        for (int64_t k = 0; k < cl; k++)
+          if (k == 0 ? !t_name_start(content[k]) : !t_name_continue(content[k])) return -7;   /* invalid capture name */
+        ADD_GROUP(name_to_group(P, content, cl));
+      }
+      i = close + 1; literal_start = i;
+    } else if (next == '0') { ADD_GROUP(0); i += 2; literal_start = i; }
+    else if (next >= '1' && next <= '9') {
+      int64_t index = next - '0', consumed = 2;
+      if (i + 2 < n && t[i + 2] >= '0' && t[i + 2] <= '9') { index = index * 10 + (t[i + 2] - '0'); consumed = 3; }
+      ADD_GROUP(index);
+      i += consumed; literal_start = i;
+    } else if (t_name_start(next)) {
+      int64_t end = i + 2;
+      while (end < n && t_name_continue(t[end])) end++;
+      ADD_GROUP(name_to_group(P, t + i + 1, end - (i + 1)));
+      i = end; literal_start = i;
+    } else { ADD(SEG_LIT, -1, 1); i++; literal_start = i; }
+  }
+  if (i > literal_start) ADD(SEG_LIT, literal_start, i - literal_start);
+#undef ADD
+#undef ADD_GROUP
+  return ns;
+}
+
+/* One input.  Writes at most cap bytes; returns the length of the result, or < 0 (template). */
+int64_t orc_replace_all(orc_prog* P, const uint8_t* in, int64_t l, const uint8_t* tmpl, int64_t tl, uint8_t* out, int64_t cap) {
+  orc_seg segs[256];
+  const int ns = template_parse(P, tmpl, tl, segs, 256);
+  if (ns < 0) return ns;
+  int64_t w = 0;
+#define PUT(src, cnt) do { const int64_t c_ = (cnt); if (c_ > 0) { if (w + c_ <= cap) memcpy(out + w, (src), (size_t)c_); w += c_; } } while (0)
+  int64_t offset = 0, last_end = 0;
+  int64_t rec[MAX_TAGS];
+  for (;;) {
+    const uint8_t* rem = in + offset;
+    const int64_t rl = l - offset;
+    if (orc_find(P, rem, rl, rec) != 1) break;                              /* FindBytesReuse(remaining, &r) */
+    const int64_t mlen = rec[1] - rec[0];
+    int64_t midx;                                                           /* bytes.Index(remaining, match.Match) */
+    if (mlen == 0) midx = 0;
+    else {
+      const uint8_t* q = (const uint8_t*)memmem(rem, (size_t)rl, rem + rec[0], (size_t)mlen);
+      if (!q) break;
+      midx = (int64_t)(q - rem);
+    }
+    const int64_t match_start = offset + midx, match_end = match_start + mlen;
+    PUT(in + last_end, match_start - last_end);
+    for (int s = 0; s < ns; s++) {
+      if (segs[s].group == SEG_LIT) { if (segs[s].lit_off < 0) PUT("$", 1); else PUT(tmpl + segs[s].lit_off, segs[s].lit_len); }
+      else { const int g = segs[s].group; if (rec[2 * g] >= 0) PUT(rem + rec[2 * g], rec[2 * g + 1] - rec[2 * g]); }
+    }
+    last_end = match_end;
+    if (mlen > 0) offset = match_end;
+    else if (match_end < l) offset = match_end + 1;
+    else break;
+  }
+  PUT(in + last_end, l - last_end);
+#undef PUT
+  return w;
+}
+
+/* Batch: out_offs[n+1]; writes results back to back while they fit in cap; returns the total length or < 0. */
+int64_t orc_replace_batch(orc_prog* P, const uint8_t* bytes, const uint64_t* offs, uint64_t n, const uint8_t* tmpl, int64_t tl,
+                          uint8_t* out, int64_t cap, uint64_t* out_offs) {
+  int64_t w = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    out_offs[i] = (uint64_t)w;
+    const int64_t r = orc_replace_all(P, bytes + offs[i], (int64_t)(offs[i + 1] - offs[i]), tmpl, tl, out + (w < cap ? w : cap), w < cap ? cap - w : 0);
+    if (r < 0) return r;
+    w += r;
+  }
+  out_offs[n] = (uint64_t)w;
+  return w;
+}

@@ -51,6 +51,10 @@ _SIGS = {
     "rgx_match_multi_dev": (C.c_int, [_P, _P, C.c_uint32, _P, _P, _P, _P]),
     "rgx_find_batch": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
     "rgx_find_batch_dev": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P, _P]),
+    "rgx_replace_batch": (C.c_int, [_P, _P, C.c_char_p, C.c_uint64, _P, _P, C.c_uint64, _P, C.c_uint64, _P, C.POINTER(C.c_uint64)]),
+    "rgx_replace_batch_dev": (C.c_int, [_P, _P, C.c_char_p, C.c_uint64, _P, _P, C.c_uint64, _P, C.c_uint64, _P, C.POINTER(C.c_uint64)]),
+    "rgx_replace_template_check": (C.c_int, [_P, C.c_char_p, C.c_uint64]),
+    "rgx_replace_template_dump": (C.c_int64, [_P, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t]),
     "rgx_find_all": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, C.c_uint64]),
     "rgx_find_all_rle": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rgx_find_all_dev": (C.c_int64, [_P, _P, _P, C.c_uint64, C.c_int64, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),

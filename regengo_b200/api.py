@@ -204,6 +204,41 @@ class Pattern:
         found, rec = self.find_batch([data])
         return Result(data, rec[0], self.group_names) if found[0] else None
 
+    # ---- ReplaceAllBytesAppend ----
+    def replace_all_batch(self, inputs, template, offsets=None):
+        """Batched ReplaceAllBytesAppend (replace.go:192-273) -> (out_bytes uint8[], out_offs uint64[n + 1])."""
+        data, offs = (pack_inputs(inputs) if offsets is None else (_as_u8(inputs), np.ascontiguousarray(offsets, dtype=np.uint64)))
+        t = template.encode("utf-8") if isinstance(template, str) else bytes(template)
+        n = offs.size - 1
+        L = _lib.load()
+        out_offs = np.zeros(n + 1, dtype=np.uint64)
+        total = C.c_uint64()
+        cap = int(data.size) + 64 * max(n, 1)
+        for _ in range(2):
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            rc = L.rgx_replace_batch(context(self.device), self._h, t, len(t), data.ctypes.data, offs.ctypes.data, n, out.ctypes.data,
+                                     cap, out_offs.ctypes.data, C.byref(total))
+            if rc != _lib.RGX_ECAPACITY:
+                break
+            cap = int(total.value)
+        check(rc)
+        return out[: int(total.value)], out_offs
+
+    def replace_all(self, data, template):
+        """ReplaceAllBytes(input, template) -> bytes."""
+        out, _ = self.replace_all_batch([bytes(data)], template)
+        return out.tobytes()
+
+    def template_segments(self, template):
+        """replace.Parse + name/index resolution (host only): [(group or -1, literal bytes)]."""
+        import json as _json
+        t = template.encode("utf-8") if isinstance(template, str) else bytes(template)
+        L = _lib.load()
+        n = check(L.rgx_replace_template_dump(self._h, t, len(t), None, 0))
+        buf = C.create_string_buffer(int(n) + 1)
+        check(L.rgx_replace_template_dump(self._h, t, len(t), buf, int(n) + 1))
+        return [(g, bytes.fromhex(h)) for g, h in _json.loads(buf.value.decode())]
+
     def device_plan(self):
         """How the device kernels will run this pattern (host computation; dict)."""
         import json as _json

@@ -10,6 +10,7 @@ SOURCES = [
     "frontend/syntax.cpp",
     "frontend/program.cpp",
     "blob.cpp",
+    "replace_template.cpp",
     "capi_host.cpp",
     "device_program.cu",
     "capi_device.cu",

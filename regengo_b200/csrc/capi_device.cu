@@ -21,6 +21,8 @@
 #include "kernels_emit.cuh"
 #include "kernels_btrun.cuh"
 #include "kernels_stream.cuh"
+#include "kernels_replace.cuh"
+#include "replace_template.hpp"
 
 using namespace rgx;
 
@@ -43,6 +45,7 @@ struct rgx_ctx {
   int64_t launches = 0;
   // grow-only scratch
   DevBuf stack, cstack, visited, small, in_bytes, in_offs, out_flag, out_rec, out_reps, out_aux;
+  DevBuf rp_tmpl, rp_len, rp_offs, rp_out;   // replace batch: template image, per-input lengths, host-call output staging
   DevBuf mm_tab;                       // match_multi: metas | image pointers | item_base | prog_first
   std::vector<uint8_t> mm_key;         // host copy of the last table uploaded (skips the upload when nothing changed)
   DevBuf fa_count, fa_keys, fa_caps, fa_reps, ch_a, ch_b, ch_sel, ch_reps, ch_selbase, ch_repsbase, ch_segsel, ch_segreps, ch_entry, ch_tile;
@@ -358,7 +361,7 @@ void rgx_ctx_destroy(rgx_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->stack, &c->cstack, &c->visited, &c->small, &c->in_bytes, &c->in_offs, &c->out_flag, &c->out_rec,
-                    &c->out_reps, &c->out_aux, &c->mm_tab, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
+                    &c->out_reps, &c->out_aux, &c->mm_tab, &c->rp_tmpl, &c->rp_len, &c->rp_offs, &c->rp_out, &c->fa_count, &c->fa_keys, &c->fa_caps, &c->fa_reps, &c->ch_a, &c->ch_b,
                     &c->ch_sel, &c->ch_reps, &c->ch_selbase, &c->ch_repsbase, &c->ch_segsel, &c->ch_segreps, &c->ch_entry, &c->ch_tile};
   for (DevBuf* b : bufs) free_buf(*b);
   if (c->h_small) cudaFreeHost(c->h_small);
@@ -565,6 +568,7 @@ int rgx_match_multi(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_prog
 
 #include "capi_findall.inc"
 #include "capi_stream.inc"
+#include "capi_replace.inc"
 
 extern "C" {
 

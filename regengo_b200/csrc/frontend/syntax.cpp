@@ -129,6 +129,24 @@ static bool unicode_table(const std::string& name, std::vector<int32_t>& pairs) 
   return false;
 }
 
+// unicode.IsLetter / unicode.IsDigit for the replace-template parser (replace_template.cpp)
+static bool rune_in_table(const char* name, int32_t r) {
+  for (const UniTable& t : kUniTables)
+    if (std::string(name) == t.name) {
+      int lo = 0, hi = t.n_pairs - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) / 2;
+        if (r < t.pairs[2 * mid]) hi = mid - 1;
+        else if (r > t.pairs[2 * mid + 1]) lo = mid + 1;
+        else return true;
+      }
+      return false;
+    }
+  return false;
+}
+bool rune_is_letter(int32_t r) { return rune_in_table("L", r); }
+bool rune_is_digit(int32_t r) { return rune_in_table("Nd", r); }
+
 static const std::vector<int32_t> kPerlD = {'0', '9'};
 static const std::vector<int32_t> kPerlS = {'\t', '\n', '\f', '\r', ' ', ' '};
 static const std::vector<int32_t> kPerlW = {'0', '9', 'A', 'Z', '_', '_', 'a', 'z'};

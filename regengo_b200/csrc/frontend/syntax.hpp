@@ -76,6 +76,10 @@ bool parse(const std::string& pattern, uint32_t flags, Arena& arena, Regexp** ou
 Regexp* simplify(Regexp* re, Arena& arena);
 bool compile(Regexp* re, Prog& prog, std::string& err);
 
+// unicode.IsLetter / unicode.IsDigit over the same tables as \p{L} / \p{Nd} (used by the replace-template parser)
+bool rune_is_letter(int32_t r);
+bool rune_is_digit(int32_t r);
+
 std::string regexp_to_string(const Regexp* re);  // debug dump (not Go's String())
 
 }  // namespace rgx
