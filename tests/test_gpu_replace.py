@@ -93,7 +93,7 @@ def test_capacity_protocol_and_device_pointers():
     data, offs = rg.pack_inputs(inputs)
     exp, eoffs = o.replace_batch(data, offs, "<$user at $domain>")
     dev = torch.device("cuda", 0)
-    d_data = torch.from_numpy(data).to(dev)
+    d_data = torch.from_numpy(data.copy()).to(dev)
     d_offs = torch.from_numpy(offs.view(np.int64)).to(dev)
     n = len(inputs)
     d_out_offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
