@@ -182,6 +182,9 @@ std::string err_bits(int e) {
   if (e & ERR_VISITED) s += " visited";
   if (e & ERR_RANGE) s += " offset-range";
   if (e & ERR_SLAB) s += " record-slab";
+  if (e & ERR_DENSE) s += " dense-input";
+  if (e & ERR_HALO) s += " halo";
+  if (e & ERR_INTERNAL) s += " internal-invariant";
   return s;
 }
 

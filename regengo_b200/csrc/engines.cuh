@@ -20,7 +20,7 @@ namespace rgx {
 enum { OP_ALT = 0, OP_ALTMATCH, OP_CAPTURE, OP_EMPTY, OP_MATCH, OP_FAIL, OP_NOP, OP_RUNE, OP_RUNE1, OP_ANY, OP_ANYNOTNL };
 enum { EMPTY_BEGIN_LINE = 1, EMPTY_END_LINE = 2, EMPTY_BEGIN_TEXT = 4, EMPTY_END_TEXT = 8, EMPTY_WORD = 16, EMPTY_NOWORD = 32 };
 enum { MODE_MATCH = 0, MODE_FIND = 1, MODE_FINDALL = 2 };
-enum { ERR_STACK = 1, ERR_CSTACK = 2, ERR_VISITED = 4, ERR_RANGE = 8, ERR_SLAB = 16, ERR_DENSE = 32, ERR_HALO = 64 };
+enum { ERR_STACK = 1, ERR_CSTACK = 2, ERR_VISITED = 4, ERR_RANGE = 8, ERR_SLAB = 16, ERR_DENSE = 32, ERR_HALO = 64, ERR_INTERNAL = 128 /* an invariant of a parallel formulation did not hold */ };
 
 constexpr int32_t CAP_ZERO = INT32_MIN;  // a capture still holding Go's zero value (absolute 0)
 

@@ -144,6 +144,7 @@ __global__ void exclusive_scan_u64_kernel(const uint64_t n, const unsigned long 
 //   RECORDS one lane per listed match re-runs that single attempt on chunk[searchPos:] for the captures.
 // Every step is the reference's own; only the order of evaluation differs.
 constexpr uint32_t RT_SLOW_REACH = 127, RT_SLOW_VAL = 255;
+constexpr int RT_TILE = 2048;   // positions per tile of the chase (one warp; 64 per lane)
 
 __device__ __forceinline__ Scratch scratch_of(const ScratchPlan& sp) {
   Scratch sc;
@@ -552,6 +553,8 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
   if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
   const Scratch sc = scratch_of(sp);
   const int lane = threadIdx.x & 31;
+  __shared__ __align__(16) uint16_t Etile[4][RT_TILE];
+  __shared__ unsigned long long Mtile[4][32];
   const bool no_slow = *slow_flag == 0;
   for (uint64_t j = sc.tid >> 5; j < n_run; j += sp.stride >> 5) {
     const uint64_t k = first_chunk + j;
@@ -564,63 +567,210 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
     int64_t pos = 0;
     unsigned long long n = 0, w = MODE == 1 ? bases[j] : MODE == 2 ? j * cap : 0;
     const unsigned long long wend = MODE == 2 ? w + cap : cap;
-    // ---- the lanes split the chunk (see chase_range) ----
-    const int64_t sub = (((data_len + 31) / 32) + 63) & ~(int64_t)63;
-    if (no_slow && sub >= 1024) {
-      ChaseRange r;
-      r.sync = -1; r.end = data_len;
-      const int64_t s0 = (int64_t)lane * sub;
-      if (lane == 0) r.sync = 0;
-      else if (s0 < data_len) {
-        int64_t cover = s0 + 254;
-        const int64_t scan_end = min(data_len, s0 + sub);
-        for (int64_t a = s0; a < scan_end;) {
-          if (a >= cover) { r.sync = a; break; }
-          const uint32_t e = tab[a];
-          const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
-          cover = max(cover, a + (int64_t)max(r7, v));
-          a += (!(e & 0x8000u) && r7 == 1u && v > 1u) ? (int64_t)v : 1;   // a run of bytes that cannot start a match is one step
-        }
-      }
-      const uint32_t valid = __ballot_sync(0xFFFFFFFFu, r.sync >= 0);
-      const uint32_t higher = lane == 31 ? 0u : (valid >> (lane + 1)) << (lane + 1);
-      const int64_t nxt = __shfl_sync(0xFFFFFFFFu, r.sync, higher ? __ffs(higher) - 1 : lane);
-      if (higher) r.end = nxt;
-      const bool on = r.sync >= 0;
-      // 1. every lane replays its range (searchPos of the first match unknown yet: nothing written)
-      const ChaseOut mo = replay_lanes<false>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, on, false, true, r, 0, -1, 0, sc, err,
-                                              nullptr, 0, 0);
-      // 2. true searchPos entering each range: the last match end before it (0: none)
-      int64_t run = mo.last_mend;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int64_t y = __shfl_up_sync(0xFFFFFFFFu, run, o); if (lane >= o) run = max(run, y); }
-      const int64_t prev = __shfl_up_sync(0xFFFFFFFFu, run, 1);
-      const int64_t pos_entry = lane == 0 ? 0 : max(prev, (int64_t)0);
-      // 3. prologues (count)
-      const bool pro = on && mo.first_a >= 0 && pos_entry < r.sync;
-      const ChaseOut po = replay_lanes<false>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, pro, true, false, r, pos_entry, mo.first_a,
-                                              mo.first_len, sc, err, nullptr, 0, 0);
-      // a range that ran into the deferral line ends the chunk: later ranges report nothing
-      unsigned long long cnt = po.broke ? po.n : po.n + mo.n;
-      const uint32_t bm = __ballot_sync(0xFFFFFFFFu, po.broke || mo.broke);
-      if (bm && lane > __ffs(bm) - 1) cnt = 0;
-      unsigned long long incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
-      const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      if (MODE == 2 && total > cap) { if (lane == 0) { atomicOr(err, ERR_SLAB); counts[j] = total; } continue; }
-      // 4. the same again, writing
-      if (MODE != 0 && total)
-        replay_lanes<true>(m, img, chunk, tab, data_len, full, (int64_t)cp.L, cstart, k, on && cnt > 0, pro, true, r, pos_entry, mo.first_a, mo.first_len,
-                           sc, err, hits, w + incl - cnt, wend);
-      if (MODE != 1 && lane == 0) counts[j] = total;
-      continue;
-    }
-    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int*>(slow_flag)) + 1, 1ull);   // statistics: chunks replayed sequentially
+    // ---- TILE CHASE: the chunk in tiles of RT_TILE positions, entries staged in shared memory ----
+    // Warp-uniform state: pos = searchPos, cur = position of the next attempt, cover = max over every position a' before
+    // the tile of a' + extent(a') (exact, or an over-estimate: that only delays sync points).  Per tile:
+    //   1. one coalesced load of the tile's entries; lane i owns the unit of 64 positions [P + 64 i, P + 64 i + 64);
+    //   2. unit reach m_i = max (a + extent(a)) over its entries, exclusive prefix maximum over the lanes -> the cover
+    //      entering each unit -> the unit's FIRST SYNC POINT (see above: a position every replay from before it visits);
+    //      the lane that owns cur starts there instead;
+    //   3. every lane with a start chases the entries up to the next lane's start (it must arrive exactly there) -- all
+    //      lanes at once, a handful of shared-memory reads each; counts and last match ends give every match its
+    //      searchPos (the end of the match before it, in order);
+    //   4. the same chase again, now testing each match the way the reference does: text located by bytes.Index from
+    //      searchPos (Q16) and the deferral rule.  A match that is deferred ends the chunk; a match whose text occurs
+    //      earlier is an EVENT: everything before the first event in order is final and written out, then the event is
+    //      reported where bytes.Index finds it, searchPos moves behind that copy and the tiles restart there (with the
+    //      conservative cover cur + 254), exactly as the reference searches on.
+    // Attempts at positions >= data_len - 127 may look past the chunk end: the sequential form below takes over there.
+    int64_t cur = 0;
     bool stop = false;
+    if (no_slow && data_len >= 2 * RT_TILE && data_len < (1ll << 30)) {
+      // (positions are chunk-relative 32-bit integers in here)
+      uint16_t* E = Etile[threadIdx.x >> 5];
+      unsigned long long* MM = Mtile[threadIdx.x >> 5];   // match entries of each unit, one bit per position
+      const int dl = (int)data_len;
+      const int lim = dl - 127;
+      const int P0 = -(int)(((uintptr_t)tab >> 1) & 7u);     // tile bases keep the 16-byte alignment of the table loads
+      int P = P0, cover = 0, cu = 0, sp_w = 0;               // cu = cur, sp_w = pos (searchPos)
+      const int defer_line = dl - (int)cp.L;
+      // A straight-line program matches at q exactly when the bytes at q pass its S steps, so a copy of a match's text
+      // IS a match entry: bytes.Index only has to look at the match entries between searchPos and the match.
+      const bool copies_are_matches = m.sl_n > 0;
+      auto hop_of = [](const uint32_t e) -> int {   // a run of bytes that cannot start a match is one step
+        const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
+        return (!(e & 0x8000u) && r7 == 1u && v > 1u) ? (int)v : 1;
+      };
+      // first copy of the text at ta (length tl) in [from, ta), or ta
+      auto index_of = [&](const int from, const int ta, const int tl) -> int {
+        if (copies_are_matches && from >= P) {
+          for (int u = (from - P) >> 6; u <= (ta - 1 - P) >> 6 && from < ta; u++) {
+            unsigned long long mk = MM[u];
+            const int ub0 = P + 64 * u;
+            if (from > ub0) mk &= ~0ull << (from - ub0);
+            if (ta < ub0 + 64) mk &= (1ull << (ta - ub0)) - 1ull;
+            while (mk) {
+              const int q = ub0 + __ffsll((long long)mk) - 1;
+              mk &= mk - 1;
+              if (same_text(chunk, q, ta, tl)) return q;
+            }
+          }
+          return ta;
+        }
+        return (int)table_index_of_text(chunk, tab, from, ta, tl);
+      };
+      while (!stop && cu < lim) {
+        const int tile_end = min(P + RT_TILE, dl);
+        // 1. entries (positions outside [0, data_len) read as 0 and are never used)
+#pragma unroll
+        for (int q = 0; q < RT_TILE / 256; q++) {
+          const int i0 = P + q * 256 + lane * 8;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (i0 >= 0 && i0 < dl) v = *reinterpret_cast<const uint4*>(tab + i0);
+          else if (i0 < 0 && i0 + 8 > 0) {
+            uint16_t t8[8];
+            for (int z = 0; z < 8; z++) t8[z] = i0 + z >= 0 ? tab[i0 + z] : (uint16_t)0;
+            v = make_uint4(t8[0] | ((uint32_t)t8[1] << 16), t8[2] | ((uint32_t)t8[3] << 16), t8[4] | ((uint32_t)t8[5] << 16), t8[6] | ((uint32_t)t8[7] << 16));
+          }
+          *reinterpret_cast<uint4*>(E + q * 256 + lane * 8) = v;
+        }
+        __syncwarp();
+        // 2. unit reach and match mask, cover entering the unit, start of the lane's chase
+        const int ub = P + 64 * lane, ue = min(ub + 64, tile_end);
+        int mreach = 0;
+        unsigned long long mm = 0;
+        for (int j = max(ub, 0); j < ue;) {
+          const uint32_t e = E[j - P];
+          mreach = max(mreach, j + (int)max((e >> 8) & 0x7Fu, e & 0xFFu));
+          if (e & 0x8000u) mm |= 1ull << (j - ub);
+          j += hop_of(e);
+        }
+        MM[lane] = mm;
+        __syncwarp();
+        int incl = mreach;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl = max(incl, y); }
+        const int before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        const int cin = lane == 0 ? cover : max(cover, before);
+        const int lane_cur = (cu - P) >> 6;
+        int start = -1;
+        if (lane == lane_cur) start = cu;
+        else if (lane > lane_cur) {
+          int lc = cin;
+          for (int j = ub; j < ue && j < lim;) {
+            if (lc <= j) { start = j; break; }
+            const uint32_t e = E[j - P];
+            lc = max(lc, j + (int)max((e >> 8) & 0x7Fu, e & 0xFFu));
+            j += hop_of(e);
+          }
+        }
+        const uint32_t startm = __ballot_sync(0xFFFFFFFFu, start >= 0);
+        const uint32_t higher = lane == 31 ? 0u : (startm >> (lane + 1)) << (lane + 1);
+        const int nstart = __shfl_sync(0xFFFFFFFFu, start, higher ? __ffs(higher) - 1 : lane);
+        const int e_end = higher ? nstart : min(tile_end, lim);
+        // 3. chase: matches and the last match end of every lane
+        uint32_t n_l = 0;
+        int last_mend = -1, a = start;
+        if (start >= 0)
+          while (a < e_end) {
+            const uint32_t e = E[a - P];
+            if (e & 0x8000u) { n_l++; last_mend = a + (int)(e & 0xFFu); }
+            a += (int)(e & 0xFFu);
+          }
+        if (start >= 0 && higher && a != e_end) atomicOr(err, ERR_INTERNAL);   // (a sync point is visited by every replay)
+        const int exit_a = a;
+        int lm = last_mend;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, lm, o); if (lane >= o) lm = max(lm, y); }
+        const int lm_before = __shfl_up_sync(0xFFFFFFFFu, lm, 1);
+        const int sp_in = lane == 0 ? sp_w : max(sp_w, lm_before);
+        const int lm_all = __shfl_sync(0xFFFFFFFFu, lm, 31);
+        // 4. the reference's tests per match, in lane order
+        uint32_t k_l = 0;
+        int ev = 0;                       // 1: deferred (the chunk ends), 2: the text occurs earlier
+        int ev_q = 0, ev_a = 0, ev_len = 0, ev_sp = 0;
+        if (n_l) {
+          int sp = sp_in;
+          a = start;
+          while (a < e_end) {
+            const uint32_t e = E[a - P];
+            const int v = (int)(e & 0xFFu);
+            if (e & 0x8000u) {
+              const int q = index_of(sp, a, v);
+              if (full && q + v > defer_line) { ev = 1; break; }
+              if (q < a) { ev = 2; ev_q = q; ev_a = a; ev_len = v; ev_sp = sp; break; }
+              k_l++;
+              sp = a + v;
+            }
+            a += v;
+          }
+        }
+        const uint32_t evm = __ballot_sync(0xFFFFFFFFu, ev != 0);
+        const int F = evm ? __ffs(evm) - 1 : 32;
+        const uint32_t valid = lane < F ? n_l : lane == F ? k_l : 0u;
+        uint32_t vincl = valid;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, vincl, o); if (lane >= o) vincl += y; }
+        const uint32_t vtotal = __shfl_sync(0xFFFFFFFFu, vincl, 31);
+        const int evF = __shfl_sync(0xFFFFFFFFu, ev, F & 31);
+        const bool reloc = F < 32 && evF == 2;
+        if (MODE == 2 && w + vtotal + (reloc ? 1u : 0u) > wend) { if (lane == 0) atomicOr(err, ERR_SLAB); n += vtotal + 1; stop = true; break; }
+        if (MODE != 0 && valid) {
+          unsigned long long wi = w + vincl - valid;
+          int sp = sp_in;
+          uint32_t left = valid;
+          a = start;
+          while (left) {
+            const uint32_t e = E[a - P];
+            const int v = (int)(e & 0xFFu);
+            if (e & 0x8000u) {
+              if (wi < wend) {
+                ReaderHit h;
+                h.search_abs = (long long)cstart + sp; h.d_true = (uint32_t)(a - sp); h.d_text = (uint32_t)(a - sp); h.chunk = k;
+                hits[wi] = h;
+              }
+              wi++; left--;
+              sp = a + v;
+            }
+            a += v;
+          }
+        }
+        w += vtotal; n += vtotal;
+        if (F == 32) {
+          // the tile is done: on to the next one
+          if (lm_all >= 0) sp_w = max(sp_w, lm_all);
+          const int last = 31 - __clz((int)startm);
+          cu = __shfl_sync(0xFFFFFFFFu, exit_a, last);
+          cover = max(cover, __shfl_sync(0xFFFFFFFFu, incl, 31));
+          P += RT_TILE;
+        } else if (!reloc) {
+          stop = true;     // too close to the boundary: the next chunk's job (and everything behind it)
+        } else {
+          const int q = __shfl_sync(0xFFFFFFFFu, ev_q, F), ta = __shfl_sync(0xFFFFFFFFu, ev_a, F);
+          const int tl = __shfl_sync(0xFFFFFFFFu, ev_len, F), tsp = __shfl_sync(0xFFFFFFFFu, ev_sp, F);
+          if (MODE != 0 && w < wend && lane == 0) {
+            ReaderHit h;
+            h.search_abs = (long long)cstart + tsp; h.d_true = (uint32_t)(ta - tsp); h.d_text = (uint32_t)(q - tsp); h.chunk = k;
+            hits[w] = h;
+          }
+          w++; n++;
+          sp_w = q + tl; cu = sp_w;
+          P = P0 + ((cu - P0) & ~63);
+          cover = cu + 254;
+        }
+        __syncwarp();
+      }
+      pos = sp_w; cur = cu;
+      if (!stop && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int*>(slow_flag)) + 2, 1ull);   // statistics: chunks on the tile chase
+    } else {
+      if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int*>(slow_flag)) + 1, 1ull);   // statistics: chunks replayed sequentially
+    }
+    // the sequential form: the whole chunk, or what the tiles left (searchPos pos, next attempt at cur)
+    bool resume = true;
     while (!stop && pos < data_len) {
       // FindBytesReuse(chunk[pos:data_len]): attempts at pos, f+1, ...
-      int64_t a = pos, mlen = -1;
+      int64_t a = resume ? max(cur, pos) : pos, mlen = -1;
+      resume = false;
       int64_t wb = -64;
       uint32_t ew = 0;
       while (a < data_len) {
