@@ -273,6 +273,51 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
   if (any_slow) *slow_flag = 1;   // some entry says "decide inline": the chase keeps to the sequential form
 }
 
+// Bit planes of one unit of 64 attempt positions of a STRAIGHT-LINE program from the unit's 96 bytes (bw[24], bytes
+// that do not exist = 0xFF): cand = positions whose byte passes step 0, alive = positions that pass all S steps (the
+// matches, length S), pl[0..5] = the number of steps survived, bit-sliced (an attempt that survives cnt < S steps
+// fails at offset cnt: the next attempt starts cnt + 1 further, and it looked at cnt + 1 bytes).
+__device__ __forceinline__ void linear_unit_planes(const DevMeta& m, const uint8_t* cm, uint32_t* bw, unsigned long long& cand,
+                                                   unsigned long long& alive, unsigned long long* pl) {
+  const int S = m.sl_n, ncls = m.sl_ncls;
+#pragma unroll
+  for (int q = 0; q < 24; q++) {
+    const uint32_t x = bw[q];
+    bw[q] = (uint32_t)cm[x & 255u] | ((uint32_t)cm[(x >> 8) & 255u] << 8) | ((uint32_t)cm[(x >> 16) & 255u] << 16) |
+            ((uint32_t)cm[x >> 24] << 24);
+  }
+  // per class: a 96-bit mask (lo: positions 0..63, hi: 64..95)
+  unsigned long long mlo[8];
+  uint32_t mhi[8];
+  for (int k = 0; k < ncls; k++) {
+    unsigned long long lo = 0;
+    uint32_t hi = 0;
+#pragma unroll
+    for (int q = 0; q < 24; q++) {
+      const uint32_t t = (bw[q] >> k) & 0x01010101u;                    // bit 0 of each byte
+      const uint32_t nib = ((t * 0x10204080u) >> 28) & 0xFu;            // -> 4 consecutive bits, byte 0 lowest
+      if (q < 16) lo |= (unsigned long long)nib << (4 * q); else hi |= nib << (4 * (q - 16));
+    }
+    mlo[k] = lo; mhi[k] = hi;
+  }
+  alive = ~0ull; cand = 0;
+  unsigned long long pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, pl4 = 0, pl5 = 0;
+  for (int i = 0; i < S; i++) {
+    const int k = m.sl_cls[i];
+    const unsigned long long sh = i == 0 ? mlo[k] : ((mlo[k] >> i) | ((unsigned long long)mhi[k] << (64 - i)));
+    alive &= sh;
+    if (i == 0) cand = alive;
+    unsigned long long carry = alive, t;
+    t = pl0 & carry; pl0 ^= carry; carry = t;
+    t = pl1 & carry; pl1 ^= carry; carry = t;
+    t = pl2 & carry; pl2 ^= carry; carry = t;
+    t = pl3 & carry; pl3 ^= carry; carry = t;
+    t = pl4 & carry; pl4 ^= carry; carry = t;
+    pl5 ^= carry;
+  }
+  pl[0] = pl0; pl[1] = pl1; pl[2] = pl2; pl[3] = pl3; pl[4] = pl4; pl[5] = pl5;
+}
+
 // The same table for a STRAIGHT-LINE program (device_program.cu: sl_*), bit-parallel: a thread owns 64
 // positions; for each byte class one bit mask over its 64 + S - 1 bytes; "the attempt at position j survives
 // step i" is bit j of AND_i (mask[class_i] >> i); the number of steps survived (= failure offset - start) is
@@ -539,7 +584,7 @@ __device__ __forceinline__ ChaseOut replay_lanes(const DevMeta& m, const uint32_
 // One WARP per chunk.  The replay is sequential, but its memory accesses are not: the lanes fetch 32 table
 // entries at a time (one coalesced load) and the attempt chain is followed through them with shuffles; the
 // bytes.Index scan tests 32 positions per step.  All control flow is warp-uniform.
-template <int MODE>
+template <int MODE, bool LINEAR>
 __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                 const uint8_t* __restrict__ d_stream, const uint64_t base_off,
                                                                 const uint16_t* __restrict__ table, const ChunkPlan cp,
@@ -555,7 +600,7 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
   const int lane = threadIdx.x & 31;
   __shared__ __align__(16) uint16_t Etile[4][RT_TILE];
   __shared__ unsigned long long Mtile[4][32];
-  const bool no_slow = *slow_flag == 0;
+  const bool no_slow = LINEAR || *slow_flag == 0;
   for (uint64_t j = sc.tid >> 5; j < n_run; j += sp.stride >> 5) {
     const uint64_t k = first_chunk + j;
     uint64_t cstart, dlen;
@@ -585,7 +630,206 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
     // Attempts at positions >= data_len - 127 may look past the chunk end: the sequential form below takes over there.
     int64_t cur = 0;
     bool stop = false;
-    if (no_slow && data_len >= 2 * RT_TILE && data_len < (1ll << 30)) {
+    if (LINEAR && data_len >= 2 * RT_TILE && data_len < (1ll << 30)) {
+      // ---- the same for a STRAIGHT-LINE program, without a table: every lane computes the bit planes of its unit from
+      // the unit's 96 bytes (linear_unit_planes) and the chase reads the attempt at a position off them: match iff the
+      // `alive` bit is set (length S), else next attempt cnt + 1 further (cnt = steps survived; 0 for a byte that cannot
+      // start a match).  Cover uses the bound S for every candidate (an over-estimate only delays sync points).
+      unsigned long long* U = reinterpret_cast<unsigned long long*>(Etile[threadIdx.x >> 5]);   // U[plane * 32 + unit]: cand, alive, pl0..pl5
+      const uint8_t* cm = reinterpret_cast<const uint8_t*>(img + m.off_sl_cm);
+      const int S = m.sl_n;
+      const int dl = (int)data_len;
+      const int lim = dl - 127;
+      const int P0 = -(int)((uintptr_t)chunk & 15u);        // unit bases keep the 16-byte alignment of the byte loads
+      int P = P0, cover = 0, cu = 0, sp_w = 0;
+      const int defer_line = dl - (int)cp.L;
+      auto steps_at = [&](const int u, const int b) -> int {   // steps survived by the attempt at unit u, bit b
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) cnt |= (int)((U[(2 + i) * 32 + u] >> b) & 1ull) << i;
+        return cnt;
+      };
+      // first copy of the text at ta in [from, ta), or ta: a copy of a match's text is itself a match entry
+      auto index_of = [&](const int from, const int ta) -> int {
+        if (from >= P) {
+          for (int u = (from - P) >> 6; u <= (ta - 1 - P) >> 6 && from < ta; u++) {
+            unsigned long long mk = U[32 + u];
+            const int ub0 = P + 64 * u;
+            if (from > ub0) mk &= ~0ull << (from - ub0);
+            if (ta < ub0 + 64) mk &= (1ull << (ta - ub0)) - 1ull;
+            while (mk) {
+              const int q = ub0 + __ffsll((long long)mk) - 1;
+              mk &= mk - 1;
+              if (same_text(chunk, q, ta, S)) return q;
+            }
+          }
+          return ta;
+        }
+        return (int)index_of_text(chunk, from, ta, S);
+      };
+      // one step of the replay at position a (< limit): returns the next position, *hit = a match starts at a
+      auto step_at = [&](const int a, const int limit, bool* hit) -> int {
+        const int u = (a - P) >> 6, b = (a - P) & 63;
+        const unsigned long long cu_ = U[u] >> b;
+        *hit = false;
+        if (!(cu_ & 1ull)) {
+          // bytes that cannot start a match: on to the next one that can (the reference tries each and fails at once)
+          const int nx = cu_ ? a + __ffsll((long long)cu_) - 1 : P + 64 * (u + 1);
+          return min(nx, limit);
+        }
+        if ((U[32 + u] >> b) & 1ull) { *hit = true; return a + S; }
+        return a + steps_at(u, b) + 1;
+      };
+      while (!stop && cu < lim) {
+        const int tile_end = min(P + RT_TILE, dl);
+        const int ub = P + 64 * lane, ue = min(ub + 64, tile_end);
+        // 1. planes of my unit
+        {
+          uint32_t bw[24];
+          if (ub >= 0 && ub + 96 <= dl) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+              const uint4 v = *reinterpret_cast<const uint4*>(chunk + ub + 16 * q);
+              bw[4 * q] = v.x; bw[4 * q + 1] = v.y; bw[4 * q + 2] = v.z; bw[4 * q + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 24; q++) {
+              uint32_t x = 0;
+              for (int b = 0; b < 4; b++) {
+                const int pp = ub + 4 * q + b;
+                x |= (uint32_t)((pp >= 0 && pp < dl) ? chunk[pp] : 0xFFu) << (8 * b);
+              }
+              bw[q] = x;
+            }
+          }
+          unsigned long long cand, alive, pl[6];
+          linear_unit_planes(m, cm, bw, cand, alive, pl);
+          if (ub >= tile_end) { cand = 0; alive = 0; }
+          __syncwarp();
+          U[lane] = cand; U[32 + lane] = alive;
+#pragma unroll
+          for (int i = 0; i < 6; i++) U[(2 + i) * 32 + lane] = pl[i];
+        }
+        __syncwarp();
+        // 2. cover entering the unit, start of the lane's chase
+        const unsigned long long myc = U[lane];
+        const int mreach = myc ? ub + 63 - __clzll((long long)myc) + S : 0;
+        int incl = mreach;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl = max(incl, y); }
+        const int before = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        const int cin = lane == 0 ? cover : max(cover, before);
+        const int lane_cur = (cu - P) >> 6;
+        int start = -1;
+        if (lane == lane_cur) start = cu;
+        else if (lane > lane_cur && ub < min(tile_end, lim)) {
+          // positions of my unit with no candidate less than S before them (inside the unit) and not below the cover
+          unsigned long long blocked = myc << 1;
+          for (int sh = 1; sh < S - 1; sh <<= 1) blocked |= blocked << min(sh, S - 1 - sh);
+          unsigned long long ok = ~blocked;
+          if (cin > ub) ok = cin - ub >= 64 ? 0ull : ok & (~0ull << (cin - ub));
+          const int top = min(ue, lim) - ub;
+          if (top < 64) ok &= (1ull << top) - 1ull;
+          if (ok) start = ub + __ffsll((long long)ok) - 1;
+        }
+        const uint32_t startm = __ballot_sync(0xFFFFFFFFu, start >= 0);
+        const uint32_t higher = lane == 31 ? 0u : (startm >> (lane + 1)) << (lane + 1);
+        const int nstart = __shfl_sync(0xFFFFFFFFu, start, higher ? __ffs(higher) - 1 : lane);
+        const int e_end = higher ? nstart : min(tile_end, lim);
+        // 3. chase: matches and the last match end of every lane
+        uint32_t n_l = 0;
+        int last_mend = -1, a = start;
+        if (start >= 0)
+          while (a < e_end) {
+            bool hit;
+            const int nx = step_at(a, e_end, &hit);
+            if (hit) { n_l++; last_mend = nx; }
+            a = nx;
+          }
+        if (start >= 0 && higher && a != e_end) atomicOr(err, ERR_INTERNAL);   // (a sync point is visited by every replay)
+        const int exit_a = a;
+        int lm = last_mend;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, lm, o); if (lane >= o) lm = max(lm, y); }
+        const int lm_before = __shfl_up_sync(0xFFFFFFFFu, lm, 1);
+        const int sp_in = lane == 0 ? sp_w : max(sp_w, lm_before);
+        const int lm_all = __shfl_sync(0xFFFFFFFFu, lm, 31);
+        // 4. the reference's tests per match, in lane order
+        uint32_t k_l = 0;
+        int ev = 0, ev_q = 0, ev_a = 0, ev_sp = 0;
+        if (n_l) {
+          int sp = sp_in;
+          a = start;
+          while (a < e_end) {
+            bool hit;
+            const int nx = step_at(a, e_end, &hit);
+            if (hit) {
+              const int q = index_of(sp, a);
+              if (full && q + S > defer_line) { ev = 1; break; }
+              if (q < a) { ev = 2; ev_q = q; ev_a = a; ev_sp = sp; break; }
+              k_l++;
+              sp = nx;
+            }
+            a = nx;
+          }
+        }
+        const uint32_t evm = __ballot_sync(0xFFFFFFFFu, ev != 0);
+        const int F = evm ? __ffs(evm) - 1 : 32;
+        const uint32_t valid = lane < F ? n_l : lane == F ? k_l : 0u;
+        uint32_t vincl = valid;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, vincl, o); if (lane >= o) vincl += y; }
+        const uint32_t vtotal = __shfl_sync(0xFFFFFFFFu, vincl, 31);
+        const int evF = __shfl_sync(0xFFFFFFFFu, ev, F & 31);
+        const bool reloc = F < 32 && evF == 2;
+        if (MODE == 2 && w + vtotal + (reloc ? 1u : 0u) > wend) { if (lane == 0) atomicOr(err, ERR_SLAB); n += vtotal + 1; stop = true; break; }
+        if (MODE != 0 && valid) {
+          unsigned long long wi = w + vincl - valid;
+          int sp = sp_in;
+          uint32_t left = valid;
+          a = start;
+          while (left) {
+            bool hit;
+            const int nx = step_at(a, e_end, &hit);
+            if (hit) {
+              if (wi < wend) {
+                ReaderHit h;
+                h.search_abs = (long long)cstart + sp; h.d_true = (uint32_t)(a - sp); h.d_text = (uint32_t)(a - sp); h.chunk = k;
+                hits[wi] = h;
+              }
+              wi++; left--;
+              sp = nx;
+            }
+            a = nx;
+          }
+        }
+        w += vtotal; n += vtotal;
+        if (F == 32) {
+          if (lm_all >= 0) sp_w = max(sp_w, lm_all);
+          const int last = 31 - __clz((int)startm);
+          cu = __shfl_sync(0xFFFFFFFFu, exit_a, last);
+          cover = max(cover, __shfl_sync(0xFFFFFFFFu, incl, 31));
+          P += RT_TILE;
+        } else if (!reloc) {
+          stop = true;     // too close to the boundary: the next chunk's job (and everything behind it)
+        } else {
+          const int q = __shfl_sync(0xFFFFFFFFu, ev_q, F), ta = __shfl_sync(0xFFFFFFFFu, ev_a, F), tsp = __shfl_sync(0xFFFFFFFFu, ev_sp, F);
+          if (MODE != 0 && w < wend && lane == 0) {
+            ReaderHit h;
+            h.search_abs = (long long)cstart + tsp; h.d_true = (uint32_t)(ta - tsp); h.d_text = (uint32_t)(q - tsp); h.chunk = k;
+            hits[w] = h;
+          }
+          w++; n++;
+          sp_w = q + S; cu = sp_w;
+          P = P0 + ((cu - P0) & ~63);
+          cover = cu + 254;
+        }
+        __syncwarp();
+      }
+      pos = sp_w; cur = cu;
+      if (!stop && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(const_cast<int*>(slow_flag)) + 2, 1ull);   // statistics: chunks on the tile chase
+    } else if (!LINEAR && no_slow && data_len >= 2 * RT_TILE && data_len < (1ll << 30)) {
       // (positions are chunk-relative 32-bit integers in here)
       uint16_t* E = Etile[threadIdx.x >> 5];
       unsigned long long* MM = Mtile[threadIdx.x >> 5];   // match entries of each unit, one bit per position
@@ -774,13 +1018,13 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
       int64_t wb = -64;
       uint32_t ew = 0;
       while (a < data_len) {
-        if (a >= wb + 32) {   // fetch the 32 entries from a on
+        if (!LINEAR && a >= wb + 32) {   // fetch the 32 entries from a on
           wb = a;
           ew = wb + lane < data_len ? tab[wb + lane] : 0u;
         }
-        const uint32_t e = __shfl_sync(0xFFFFFFFFu, ew, (int)(a - wb));
+        const uint32_t e = LINEAR ? 0u : __shfl_sync(0xFFFFFFFFu, ew, (int)(a - wb));
         const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
-        if (r7 != RT_SLOW_REACH && v != RT_SLOW_VAL && a + (int64_t)r7 <= data_len) {
+        if (!LINEAR && r7 != RT_SLOW_REACH && v != RT_SLOW_VAL && a + (int64_t)r7 <= data_len) {   // (LINEAR: no table, every attempt runs the machine)
           if (e & 0x8000u) { mlen = (int64_t)v; break; }
           a += (int64_t)v;
         } else {
