@@ -616,7 +616,7 @@ class SuiteWork:
         barrier()
         dt = (time.perf_counter() - t0) / k_e2e
         assert bool((h_out == self.d_out.cpu()).all())
-        return dt, self.n_bytes + 8 * (self.n_inputs + 1), self.n_inputs, "rgx_match_multi (host buffers, 64-bit offsets converted on upload)"
+        return dt, self.n_bytes + 8 * (self.n_inputs + 1), self.n_inputs, "rgx_match_multi (host buffers: bytes and 64-bit offsets uploaded, flags downloaded)"
 
     def parity(self, window_mib):
         """Every pattern's first inputs (about a million in all) against the CPU oracle's MatchBytes."""

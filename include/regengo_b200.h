@@ -131,7 +131,7 @@ int rgx_match_batch_dev(rgx_ctx* c, const rgx_program* p, const uint8_t* d_bytes
 /* Many programs, ONE launch (BASELINE.json configs[3]: a pattern suite over a packed batch of short inputs).  The
  * inputs of program p are the index range [prog_first[p], prog_first[p+1]) of the batch (prog_first is a HOST array of
  * n_progs + 1 entries); out[i - prog_first[0]] = MatchBytes of progs[p] on input i.  Host form: 64-bit offsets as in
- * rgx_match_batch, converted to 32-bit shard-relative offsets on upload (a batch holds at most 4 GiB of bytes).
+ * rgx_match_batch, uploaded as they are (the kernel has a 64-bit-offset form).
  * Device form: d_offs32[i] is relative to d_bytes, d_out is indexed by i. */
 int rgx_match_multi(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_progs, const uint8_t* bytes,
                     const uint64_t* offs, const uint64_t* prog_first, uint8_t* out);

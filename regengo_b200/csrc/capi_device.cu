@@ -546,21 +546,19 @@ int rgx_match_multi(rgx_ctx* c, const rgx_program* const* progs, uint32_t n_prog
   if (n == 0) return RGX_OK;
   if (!out) { set_error("null argument"); return RGX_EINVAL; }
   const uint64_t base = offs[i0], total = offs[i0 + n] - base;
-  if (total > 0xFFFFFFF0ull) { set_error("rgx_match_multi: a batch holds at most 4 GiB of input bytes (32-bit shard-relative offsets); split it"); return RGX_EINVAL; }
   CU(cudaSetDevice(c->device));
   int rc;
   if ((rc = ensure(c, c->in_bytes, total + 16))) return rc;
-  if ((rc = ensure(c, c->in_offs, (n + 1) * 4))) return rc;
+  if ((rc = ensure(c, c->in_offs, (n + 1) * 8))) return rc;
   if ((rc = ensure(c, c->out_flag, n))) return rc;
-  // the ABI's 64-bit offsets become 32-bit offsets relative to the batch's first byte
-  std::vector<uint32_t> o32(n + 1);
-  for (uint64_t i = 0; i <= n; i++) o32[i] = (uint32_t)(offs[i0 + i] - base);
+  // The ABI's 64-bit offsets are uploaded as they are (no host pass over them) and the kernel's 64-bit-offset form
+  // reads them directly; the byte pointer is shifted so that offs[i0] maps to the first uploaded byte.
   std::vector<uint64_t> pf(n_progs + 1);
   for (uint32_t p = 0; p <= n_progs; p++) pf[p] = prog_first[p] - i0;
   if (total) CU(cudaMemcpyAsync(c->in_bytes.p, bytes + base, total, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaMemcpyAsync(c->in_offs.p, o32.data(), (n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
-  rc = match_multi_dev<uint32_t>(c, progs, n_progs, (const uint8_t*)c->in_bytes.p, (const uint32_t*)c->in_offs.p, pf.data(), (uint8_t*)c->out_flag.p);
+  CU(cudaMemcpyAsync(c->in_offs.p, offs + i0, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  rc = match_multi_dev<unsigned long long>(c, progs, n_progs, (const uint8_t*)c->in_bytes.p - base, (const unsigned long long*)c->in_offs.p, pf.data(),
+                                           (uint8_t*)c->out_flag.p);
   if (rc) return rc;
   CU(cudaMemcpyAsync(out, c->out_flag.p, n, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));

@@ -650,22 +650,25 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
         return cnt;
       };
       // first copy of the text at ta in [from, ta), or ta: a copy of a match's text is itself a match entry
+      unsigned long long* Mprev = Mtile[threadIdx.x >> 5];   // `alive` of the tile before this one (when prev_ok)
+      bool prev_ok = false;
       auto index_of = [&](const int from, const int ta) -> int {
-        if (from >= P) {
-          for (int u = (from - P) >> 6; u <= (ta - 1 - P) >> 6 && from < ta; u++) {
-            unsigned long long mk = U[32 + u];
-            const int ub0 = P + 64 * u;
-            if (from > ub0) mk &= ~0ull << (from - ub0);
-            if (ta < ub0 + 64) mk &= (1ull << (ta - ub0)) - 1ull;
-            while (mk) {
-              const int q = ub0 + __ffsll((long long)mk) - 1;
-              mk &= mk - 1;
-              if (same_text(chunk, q, ta, S)) return q;
-            }
+        if (from >= ta) return ta;
+        if (from < P && !(prev_ok && from >= P - RT_TILE)) return (int)index_of_text(chunk, from, ta, S);
+        // units are numbered from the previous tile's first: 0..31 previous, 32..63 this tile
+        const int base = P - RT_TILE;
+        for (int u = (from - base) >> 6; u <= (ta - 1 - base) >> 6; u++) {
+          unsigned long long mk = u < 32 ? Mprev[u] : U[u];   // (U[32 + unit] = alive)
+          const int ub0 = base + 64 * u;
+          if (from > ub0) mk &= ~0ull << (from - ub0);
+          if (ta < ub0 + 64) mk &= (1ull << (ta - ub0)) - 1ull;
+          while (mk) {
+            const int q = ub0 + __ffsll((long long)mk) - 1;
+            mk &= mk - 1;
+            if (same_text(chunk, q, ta, S)) return q;
           }
-          return ta;
         }
-        return (int)index_of_text(chunk, from, ta, S);
+        return ta;
       };
       // one step of the replay at position a (< limit): returns the next position, *hit = a match starts at a
       auto step_at = [&](const int a, const int limit, bool* hit) -> int {
@@ -811,6 +814,8 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
           cu = __shfl_sync(0xFFFFFFFFu, exit_a, last);
           cover = max(cover, __shfl_sync(0xFFFFFFFFu, incl, 31));
           P += RT_TILE;
+          Mprev[lane] = U[32 + lane];
+          prev_ok = true;
         } else if (!reloc) {
           stop = true;     // too close to the boundary: the next chunk's job (and everything behind it)
         } else {
@@ -824,6 +829,7 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
           sp_w = q + S; cu = sp_w;
           P = P0 + ((cu - P0) & ~63);
           cover = cu + 254;
+          prev_ok = false;
         }
         __syncwarp();
       }
