@@ -137,10 +137,11 @@ __global__ void exclusive_scan_u64_kernel(const uint64_t n, const unsigned long 
 //           {match:1 | reach:7 | len-or-next:8} -- reach = how far the attempt looked, len = match length or
 //           next = distance to the next attempt (for a byte that cannot start a match: to the next byte
 //           that can).  Values that do not fit mean "decide inline".
-//   CHASE   one lane per chunk replays the reference loop over the table: follow next-pointers to the first
+//   CHASE   one warp per chunk replays the reference loop over the table: follow next-pointers to the first
 //           match (inline exact attempt with the chunk's limit when an entry is marked or reaches the chunk
 //           end), locate the match text with bytes.Index from searchPos (Q16), apply the deferral rule,
-//           move searchPos.  Pass 0 counts, pass 1 lists {searchPos, attempt start, text position}.
+//           move searchPos; lists {searchPos, attempt start, text position}.  Tiles of the chunk are chased by
+//           all lanes in parallel from sync points (see below).
 //   RECORDS one lane per listed match re-runs that single attempt on chunk[searchPos:] for the captures.
 // Every step is the reference's own; only the order of evaluation differs.
 constexpr uint32_t RT_SLOW_REACH = 127, RT_SLOW_VAL = 255;
@@ -318,110 +319,6 @@ __device__ __forceinline__ void linear_unit_planes(const DevMeta& m, const uint8
   pl[0] = pl0; pl[1] = pl1; pl[2] = pl2; pl[3] = pl3; pl[4] = pl4; pl[5] = pl5;
 }
 
-// The same table for a STRAIGHT-LINE program (device_program.cu: sl_*), bit-parallel: a thread owns 64
-// positions; for each byte class one bit mask over its 64 + S - 1 bytes; "the attempt at position j survives
-// step i" is bit j of AND_i (mask[class_i] >> i); the number of steps survived (= failure offset - start) is
-// counted in bit planes.  No interpreter, no divergence.
-__global__ void __launch_bounds__(256) find_reader_table_linear_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
-                                                                       const uint8_t* __restrict__ d_stream, const uint64_t len,
-                                                                       uint16_t* __restrict__ table) {
-  extern __shared__ __align__(16) uint32_t smem_img[];
-  __shared__ __align__(8) unsigned long long mbar;
-  const uint32_t* img = gimg;
-  if (in_smem) { stage_image_tma(smem_img, gimg, m.image_words, &mbar); img = smem_img; }
-  const uint8_t* cm = reinterpret_cast<const uint8_t*>(img + m.off_sl_cm);
-  const int S = m.sl_n, ncls = m.sl_ncls;
-  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
-  const uint64_t n_units = (len + 63) / 64;
-  const bool aligned = ((uintptr_t)d_stream & 15u) == 0;
-  for (uint64_t u = tid; u < n_units; u += stride) {
-    const uint64_t p0 = u * 64;
-    const uint32_t nb = (uint32_t)min((uint64_t)64, len - p0);
-    // class bits of my 96 bytes (bytes past the end read as 0xFF: in no ASCII class)
-    uint32_t bw[24];
-    if (aligned && p0 + 96 <= len) {
-#pragma unroll
-      for (int q = 0; q < 6; q++) {
-        const uint4 v = *reinterpret_cast<const uint4*>(d_stream + p0 + 16 * q);
-        bw[4 * q] = v.x; bw[4 * q + 1] = v.y; bw[4 * q + 2] = v.z; bw[4 * q + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 24; q++) {
-        uint32_t x = 0;
-        for (int b = 0; b < 4; b++) {
-          const uint64_t pp = p0 + 4 * q + b;
-          x |= (uint32_t)(pp < len ? d_stream[pp] : 0xFFu) << (8 * b);
-        }
-        bw[q] = x;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 24; q++) {
-      const uint32_t x = bw[q];
-      bw[q] = (uint32_t)cm[x & 255u] | ((uint32_t)cm[(x >> 8) & 255u] << 8) | ((uint32_t)cm[(x >> 16) & 255u] << 16) |
-              ((uint32_t)cm[x >> 24] << 24);
-    }
-    // per class: a 96-bit mask (lo: positions 0..63, hi: 64..95)
-    unsigned long long mlo[8];
-    uint32_t mhi[8];
-    for (int k = 0; k < ncls; k++) {
-      unsigned long long lo = 0;
-      uint32_t hi = 0;
-#pragma unroll
-      for (int q = 0; q < 24; q++) {
-        const uint32_t t = (bw[q] >> k) & 0x01010101u;                    // bit 0 of each byte
-        const uint32_t nib = ((t * 0x10204080u) >> 28) & 0xFu;            // -> 4 consecutive bits, byte 0 lowest
-        if (q < 16) lo |= (unsigned long long)nib << (4 * q); else hi |= nib << (4 * (q - 16));
-      }
-      mlo[k] = lo; mhi[k] = hi;
-    }
-    // survive steps
-    unsigned long long alive = ~0ull, cand = 0;
-    unsigned long long pl0 = 0, pl1 = 0, pl2 = 0, pl3 = 0, pl4 = 0, pl5 = 0;     // steps survived, bit-sliced (S <= 32)
-    for (int i = 0; i < S; i++) {
-      const int k = m.sl_cls[i];
-      const unsigned long long sh = i == 0 ? mlo[k] : ((mlo[k] >> i) | ((unsigned long long)mhi[k] << (64 - i)));
-      alive &= sh;
-      if (i == 0) cand = alive;
-      unsigned long long carry = alive, t;
-      t = pl0 & carry; pl0 ^= carry; carry = t;
-      t = pl1 & carry; pl1 ^= carry; carry = t;
-      t = pl2 & carry; pl2 ^= carry; carry = t;
-      t = pl3 & carry; pl3 ^= carry; carry = t;
-      t = pl4 & carry; pl4 ^= carry; carry = t;
-      pl5 ^= carry;
-    }
-    // entries (16 bytes = 8 entries per store when the unit is whole: a 2-byte store per position would touch
-    // one sector per lane and position)
-    auto entry_of = [&](const uint32_t j) -> uint32_t {
-      if (!((cand >> j) & 1ull)) {
-        const unsigned long long rest = j + 1 < 64 ? cand >> (j + 1) : 0ull;
-        uint32_t dist = rest ? (uint32_t)__ffsll((long long)rest) : 64u - j;
-        if (j + dist > nb) dist = nb - j;
-        return (1u << 8) | dist;
-      }
-      const uint32_t cnt = (uint32_t)((pl0 >> j) & 1ull) | ((uint32_t)((pl1 >> j) & 1ull) << 1) | ((uint32_t)((pl2 >> j) & 1ull) << 2) |
-                           ((uint32_t)((pl3 >> j) & 1ull) << 3) | ((uint32_t)((pl4 >> j) & 1ull) << 4) | ((uint32_t)((pl5 >> j) & 1ull) << 5);
-      if (cnt == (uint32_t)S) return 0x8000u | ((uint32_t)S << 8) | (uint32_t)S;
-      return ((cnt + 1u) << 8) | (cnt + 1u);
-    };
-    if (nb == 64 && (((uintptr_t)(table + p0)) & 15u) == 0) {
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        uint4 v;
-        v.x = entry_of(8 * q) | (entry_of(8 * q + 1) << 16);
-        v.y = entry_of(8 * q + 2) | (entry_of(8 * q + 3) << 16);
-        v.z = entry_of(8 * q + 4) | (entry_of(8 * q + 5) << 16);
-        v.w = entry_of(8 * q + 6) | (entry_of(8 * q + 7) << 16);
-        *reinterpret_cast<uint4*>(table + p0 + 8 * q) = v;
-      }
-    } else {
-      for (uint32_t j = 0; j < nb; j++) table[p0 + j] = (uint16_t)entry_of(j);
-    }
-  }
-}
-
 struct ReaderHit { long long search_abs; uint32_t d_true, d_text; unsigned long long chunk; };   // stream offset of searchPos; attempt start / text position relative to it; ChunkIndex
 
 // bytes.Index(hay[from:], hay[ns:ns+nl]) by a whole warp: lane i tests from + i, from + 32 + i, ...
@@ -452,32 +349,14 @@ __device__ __forceinline__ int64_t table_index_of_text(const uint8_t* hay, const
   return ns;
 }
 
-// The chase of one chunk by the 32 lanes of a warp, each over its own range of the chunk (no entry of the table says
-// "decide inline": the caller checked).
-//
-// SYNC POINTS.  Call extent(a) = max(reach, len-or-next) of the entry at a: the attempt at a looks no further than
-// a + extent(a), and whatever the replay does at a -- fail and restart, match and continue behind the match, match
-// with the text located earlier (Q16) -- its next position is at most a + extent(a).  If every a < c has
-// a + extent(a) <= c, then c is visited by EVERY replay that starts before c: take the last visited position v < c;
-// the next one is >= c by choice of v and <= v + extent(v) <= c.  Extents are below 255 here, so a lane finds such a
-// c by scanning entries from its nominal start s with cover = s + 254.  From c on the replay depends on the past
-// only through searchPos (the end of the last match), which matters for one thing: where bytes.Index starts looking
-// for the text of the range's FIRST match.
-//   1. every lane replays [c_i, c_{i+1}) and keeps: hit count, first match (attempt start, length), last match end;
-//   2. the true searchPos entering range i is the running maximum of the last match ends before it;
-//   3. PROLOGUE of range i: while the first match's text occurs at some q in [searchPos, c_i) -- a copy that the
-//      skip-restart rule jumped over -- the reference reports the match THERE (bytes.Index), moves searchPos to
-//      q + len and searches on: that stretch [q + len, c_i) is replayed exactly (its searchPos is known), and the
-//      replay arrives at c_i again (sync point), where the first match is found once more;
-//   4. the hits are written in range order: prologue hits, then the range's own.
-//
-// All 32 lanes run ONE loop in lock-step (replay_lanes): a lane is a small state machine -- FIND (prologue: look for
-// a copy of the text), CHAIN (follow the attempts), INDEX (bytes.Index behind a match) -- and an iteration costs one
-// table entry per lane.  (Per-lane nested loops would be correct too, but the lanes of a warp then run one after
-// the other: measured 1.2 active lanes per instruction.)
-struct ChaseRange { int64_t sync, end; };
-struct ChaseOut { unsigned long long n; int64_t first_a, first_len, last_mend, spos; bool broke; };
-enum { PH_FIND = 0, PH_CHAIN = 1, PH_INDEX = 2, PH_DONE = 3 };
+// SYNC POINTS (what lets the lanes of a warp chase one chunk in parallel).  Call extent(a) = max(reach, len-or-next) of
+// the attempt at a: it looks no further than a + extent(a), and whatever the replay does at a -- fail and restart, match
+// and continue behind the match, match with the text located earlier (Q16) -- its next position is at most
+// a + extent(a).  If every a < c has a + extent(a) <= c, then c is visited by EVERY replay that starts before c: take
+// the last visited position v < c; the next one is >= c by choice of v and <= v + extent(v) <= c.  From c on the replay
+// depends on the past only through searchPos (the end of the last match), which matters for one thing: where
+// bytes.Index starts looking for the text of the next match.  The tile chase in find_reader_chase_kernel is built on
+// this; an over-estimated cover (max of a + extent(a)) only makes it find fewer sync points, never a wrong one.
 
 // does hay[q:q+nl] equal hay[np:np+nl]?
 __device__ __forceinline__ bool same_text(const uint8_t* hay, int64_t q, int64_t np, int64_t nl) {
@@ -486,104 +365,13 @@ __device__ __forceinline__ bool same_text(const uint8_t* hay, int64_t q, int64_t
   return j == nl;
 }
 
-// Warp-collective.  Lane with `on`: [prologue over [pos_entry, r.sync) for the text at first_a] then [the range
-// r.sync .. r.end], as asked.  Hits go to hits[w ...] (WRITE).  out.spos = the searchPos the range's first match sees.
-template <bool WRITE>
-__device__ __forceinline__ ChaseOut replay_lanes(const DevMeta& m, const uint32_t* __restrict__ img, const uint8_t* chunk, const uint16_t* tab,
-                                                 const int64_t data_len, const bool full, const int64_t L, const uint64_t cstart,
-                                                 const uint64_t k, const bool on, const bool do_prologue, const bool do_main,
-                                                 const ChaseRange r, const int64_t pos_entry, const int64_t first_a, const int64_t first_len,
-                                                 const Scratch& sc, int* err, ReaderHit* hits, unsigned long long w,
-                                                 const unsigned long long wend) {
-  ChaseOut o;
-  o.n = 0; o.first_a = -1; o.first_len = 0; o.last_mend = -1; o.spos = pos_entry; o.broke = false;
-  int phase = !on ? PH_DONE : do_prologue ? PH_FIND : do_main ? PH_CHAIN : PH_DONE;
-  bool in_main = !do_prologue, first = true;
-  int64_t pos = do_prologue ? pos_entry : r.sync;   // searchPos
-  int64_t a = r.sync;                                // attempt position (CHAIN) / match position (INDEX)
-  int64_t q = pos;                                   // scan position (FIND, INDEX)
-  int64_t cur_end = in_main ? r.end : r.sync, mlen = 0;
-  while (__any_sync(0xFFFFFFFFu, phase != PH_DONE)) {
-    if (phase == PH_FIND) {
-      if (q >= r.sync) {
-        // no (more) copy of the text before the sync point: the prologue is over
-        o.spos = pos;
-        if (do_main) { in_main = true; first = true; pos = r.sync; a = r.sync; cur_end = r.end; phase = PH_CHAIN; }
-        else phase = PH_DONE;
-      } else {
-        const uint32_t e = tab[q];
-        if (!(e & 0x8000u) && ((e >> 8) & 0x7Fu) == 1u && (e & 0xFFu) > 1u) q += (int64_t)(e & 0xFFu);   // bytes that cannot start the text
-        else if (same_text(chunk, q, first_a, first_len)) {
-          // bytes.Index finds this copy first: the match is reported here, searchPos moves behind it
-          const int64_t mend = q + first_len;
-          if (full && mend > data_len - L) { o.broke = true; phase = PH_DONE; }
-          else {
-            if (WRITE && w < wend) {
-              ReaderHit h;
-              h.search_abs = (long long)cstart + pos; h.d_true = (uint32_t)(first_a - pos); h.d_text = (uint32_t)(q - pos); h.chunk = k;
-              hits[w] = h;
-            }
-            w++; o.n++;
-            pos = mend; a = mend; cur_end = r.sync; phase = PH_CHAIN;   // replay [mend, sync) exactly
-          }
-        } else q++;
-      }
-    } else if (phase == PH_CHAIN) {
-      if (a >= cur_end) {
-        if (in_main) phase = PH_DONE;
-        else { q = pos; phase = PH_FIND; }           // back at the sync point: look for another copy behind searchPos
-      } else {
-        const uint32_t e = tab[a];
-        const uint32_t r7 = (e >> 8) & 0x7Fu, v = e & 0xFFu;
-        if (a + (int64_t)r7 <= data_len) {
-          if (e & 0x8000u) { mlen = (int64_t)v; q = pos; phase = PH_INDEX; }
-          else a += (int64_t)v;
-        } else {
-          // the attempt would look past the end of the chunk: decide with the chunk's own limit
-          int64_t ml = 0, ns = 0, reach = 0;
-          if (reader_attempt(m, img, chunk, data_len, a, sc, err, &ml, &ns, &reach)) { mlen = ml; q = pos; phase = PH_INDEX; }
-          else if (ns > data_len) a = data_len;
-          else a = ns;
-        }
-      }
-    } else if (phase == PH_INDEX) {
-      // bytes.Index(chunk[pos:], text): first copy of the text at or behind searchPos (the match itself at the latest)
-      bool found = q >= a;
-      if (!found) {
-        const uint32_t e = tab[q];
-        if (!(e & 0x8000u) && ((e >> 8) & 0x7Fu) == 1u && (e & 0xFFu) > 1u) q += (int64_t)(e & 0xFFu);
-        else if (same_text(chunk, q, a, mlen)) found = true;
-        else q++;
-      }
-      if (found) {
-        const int64_t mstart = q < a ? q : a, mend = mstart + mlen;
-        if (full && mend > data_len - L) { o.broke = true; phase = PH_DONE; }   // too close to the boundary: next chunk's job
-        else {
-          const int64_t spos = (in_main && first) ? o.spos : pos;
-          if (in_main && first) { o.first_a = a; o.first_len = mlen; }
-          first = false;
-          if (WRITE && w < wend) {
-            ReaderHit h;
-            h.search_abs = (long long)cstart + spos; h.d_true = (uint32_t)(a - spos); h.d_text = (uint32_t)(mstart - spos); h.chunk = k;
-            hits[w] = h;
-          }
-          w++; o.n++;
-          if (in_main) o.last_mend = mend;
-          pos = mend; a = mend; phase = PH_CHAIN;
-        }
-      }
-    }
-    __syncwarp();
-  }
-  return o;
-}
-
 // MODE 0: count per chunk.  MODE 1: list the hits at bases[chunk].  MODE 2: one pass -- list the hits of chunk j
 // at j * region (a chunk cannot hold more than `region` matches) and count them; a chunk that would overflow
 // its region sets ERR_SLAB and the caller falls back to the two-pass form.
-// One WARP per chunk.  The replay is sequential, but its memory accesses are not: the lanes fetch 32 table
-// entries at a time (one coalesced load) and the attempt chain is followed through them with shuffles; the
-// bytes.Index scan tests 32 positions per step.  All control flow is warp-uniform.
+// One WARP per chunk: tiles of RT_TILE positions chased by all lanes at once (below); the last 127 positions of a chunk,
+// short chunks and tables with "decide inline" entries take the sequential form, where the lanes fetch 32 table entries
+// at a time and the attempt chain is followed through them with shuffles.  LINEAR: a straight-line program
+// (device_program.cu: sl_*) -- no table at all, the attempts of a tile are bit planes computed from its bytes.
 template <int MODE, bool LINEAR>
 __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m, const uint32_t* __restrict__ gimg, const int in_smem,
                                                                 const uint8_t* __restrict__ d_stream, const uint64_t base_off,

@@ -99,11 +99,11 @@ def test_chunk_range_sharding_matches_whole():
 
 
 def test_lane_parallel_chase_boundaries():
-    """The chase splits a chunk over the 32 lanes of a warp at sync points (kernels_stream.cuh, chase_range).  Put the
-    cases that couple ranges exactly where ranges meet (multiples of 2 KiB in a 64 KiB chunk, of 32 KiB in a 1 MiB one):
-    dates straddling them, skip-restart prefixes, a skipped copy of a date's text far before the real match (bytes.Index
-    then reports the copy, from another lane's range: the chunk must take the sequential replay), digit runs longer than
-    a range (no sync point there), and heavy digit noise."""
+    """The chase processes a chunk in tiles of 2 KiB, every lane of a warp starting at the first sync point of its 64
+    positions (kernels_stream.cuh, TILE CHASE).  Put the cases that couple lanes and tiles exactly where they meet
+    (multiples of 2 KiB, and of 32 KiB for the 1 MiB buffer): dates straddling them, skip-restart prefixes, a skipped copy
+    of a date's text far before the real match (bytes.Index reports the copy: an EVENT that restarts the tiles behind
+    it), digit runs longer than a tile (no sync point there), and heavy digit noise."""
     p, o = pair(synth.DATE_CAPTURE_PATTERN)
     rng = np.random.default_rng(11)
     for bufsize, step in ((0, 2048), (1 << 20, 32768)):
@@ -138,3 +138,46 @@ def test_lane_parallel_chase_boundaries():
     for noise in (0.2, 0.5):
         check_reader(p, o, synth.make_buffer("stream", 2 * synth.BLOCK + 17, digit_noise=noise))
         check_reader(p, o, synth.make_buffer("stream", 2 * synth.BLOCK + 17, digit_noise=noise), 1 << 20)
+
+
+def test_tile_chase_events_engines_and_alignment():
+    """More of the tile chase: (a) relocation events in bulk -- every date preceded by a digit is jumped over by the
+    skip-restart rule and is then a COPY of a later identical date's text, so bytes.Index reports matches there and the
+    tiles restart behind them, many times per chunk; (b) straight-line programs of length 1 and 32 (table-free bit-plane
+    path) next to table-driven ones (an Alt pattern, a TDFA pattern); (c) leftovers that make the chunk stride odd, so
+    chunks start at every alignment of the 16-byte loads; (d) deferral of a match at a tile edge."""
+    rng = np.random.default_rng(23)
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    # (a) few distinct dates, a third of them behind a digit
+    dates = [b"2024-01-15", b"1999-12-31"]
+    parts = []
+    for i in range(30000):
+        d = dates[int(rng.integers(0, 2))]
+        parts.append((b"7" if rng.integers(0, 3) == 0 else b"") + d + b"x" * int(rng.integers(1, 40)))
+    buf = b"".join(parts)
+    n = check_reader(p, o, buf)
+    assert n > 20000
+    check_reader(p, o, buf, 1 << 20)
+    # (c) odd strides: BufferSize 64 KiB with leftovers 1001..1016 -> chunk starts at all 16 alignments
+    for lo in (1001, 1003, 1008, 1013):
+        check_reader(p, o, buf[: 5 * 65536 + 99], 65536, lo)
+    # (b) straight-line programs of length 1 and 32; table-driven programs through the same tiles
+    text = synth.make_buffer("stream", 3 * synth.BLOCK // 2 + 5, digit_noise=0.05)
+    for pat in (r"(\d)", r"(\d{32})", r"(\d{4})-(\d{2})", r"(\d\d-|-\d\d)", r"(?P<y>\d{4})-(?P<m>\d+)"):
+        pp, oo = pair(pat)
+        check_reader(pp, oo, text)
+        check_reader(pp, oo, text, 1 << 20)
+    long_digits = bytearray(text[:300000])
+    long_digits[5000:5100] = b"1234567890" * 10
+    long_digits[70000:70040] = b"9" * 40
+    pp, oo = pair(r"(\d{32})")
+    assert check_reader(pp, oo, bytes(long_digits)) >= 3
+    # (d) a date ending exactly on / one past the deferral line of the first chunk, which is also near a tile edge
+    pl, ol = pair(synth.DATE_CAPTURE_PATTERN)
+    B, L = ol.stream_config(0, 0)
+    for shift in (-1, 0, 1, 2):
+        b2 = bytearray(b"z" * (2 * B))
+        end = B - L + shift
+        b2[end - 10:end] = b"2024-07-04"
+        b2[2048 - 5:2048 + 5] = b"2024-08-05"
+        check_reader(pl, ol, bytes(b2))
