@@ -334,6 +334,7 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
   if (P.find_engine == FIND_BT && m.n_alt == 0 && m.n_empty == 0) {
     std::vector<Bits256> classes;
     std::vector<uint8_t> steps;
+    std::vector<int> cap_at(MAX_CAPS, -1);   // capture slot -> bytes consumed before its Capture instruction
     int pc = prog.start;
     bool ok = true, done = false;
     size_t guard = 0;
@@ -342,7 +343,10 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       Bits256 set;
       bool consumes = false;
       switch (in.op) {
-        case InstNop: case InstCapture: pc = (int)in.out; break;
+        case InstCapture:
+          if (in.arg < (uint32_t)MAX_CAPS) cap_at[in.arg] = (int)steps.size();
+          pc = (int)in.out; break;
+        case InstNop: pc = (int)in.out; break;
         case InstRune1:
           if (in.rune.size() != 1 || in.rune[0] >= 128) { ok = false; break; }
           set.set((uint32_t)in.rune[0]); consumes = true; break;
@@ -367,6 +371,12 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       m.sl_n = (int32_t)steps.size();
       m.sl_ncls = (int32_t)classes.size();
       for (size_t i = 0; i < steps.size(); i++) m.sl_cls[i] = steps[i];
+      // every capture of a straight-line program sits at a fixed distance from the match start (slots 0 / 1: the match)
+      m.sl_caps_ok = prog.num_cap <= MAX_CAPS ? 1 : 0;
+      for (int slot = 0; slot < prog.num_cap && slot < MAX_CAPS; slot++) {
+        const int at = slot == 0 ? 0 : slot == 1 ? (int)steps.size() : cap_at[slot];
+        if (at < 0) m.sl_caps_ok = 0; else m.sl_cap[slot] = (uint8_t)at;
+      }
       m.off_sl_cm = (uint32_t)w.size();
       for (uint32_t c0 = 0; c0 < 256; c0 += 4) {
         uint32_t word = 0;

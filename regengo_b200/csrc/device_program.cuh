@@ -87,6 +87,8 @@ struct DevMeta {
   int32_t sl_ncls;
   uint32_t off_sl_cm;
   uint8_t sl_cls[32];
+  uint8_t sl_cap[32];          // capture slot -> offset from the match start (valid when sl_caps_ok)
+  int32_t sl_caps_ok;
 };
 
 struct DeviceImage {

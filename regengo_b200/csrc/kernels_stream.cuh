@@ -528,17 +528,30 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
         const uint32_t higher = lane == 31 ? 0u : (startm >> (lane + 1)) << (lane + 1);
         const int nstart = __shfl_sync(0xFFFFFFFFu, start, higher ? __ffs(higher) - 1 : lane);
         const int e_end = higher ? nstart : min(tile_end, lim);
-        // 3. chase: matches and the last match end of every lane
-        uint32_t n_l = 0;
+        // 3. ONE chase per lane: matches, last match end, the first four match positions (kept in registers), and the
+        //    reference's tests for every match but the lane's first -- their searchPos is the end of the match before
+        //    them, in the same lane.  (ev: 1 = deferred, the chunk ends; 2 = the text occurs earlier)
+        uint32_t n_l = 0, k_l = 0;
         int last_mend = -1, a = start;
+        int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        int ev = 0, ev_q = 0, ev_a = 0, ev_sp = 0;
         if (start >= 0)
-          while (a < e_end) {
+          while (a < e_end && !ev) {
             bool hit;
             const int nx = step_at(a, e_end, &hit);
-            if (hit) { n_l++; last_mend = nx; }
+            if (hit) {
+              if (n_l == 0) m0 = a; else if (n_l == 1) m1 = a; else if (n_l == 2) m2 = a; else if (n_l == 3) m3 = a;
+              if (n_l) {
+                const int q = index_of(last_mend, a);
+                if (full && q + S > defer_line) ev = 1;
+                else if (q < a) { ev = 2; ev_q = q; ev_a = a; ev_sp = last_mend; }
+                else k_l++;
+              }
+              n_l++; last_mend = nx;
+            }
             a = nx;
           }
-        if (start >= 0 && higher && a != e_end) atomicOr(err, ERR_INTERNAL);   // (a sync point is visited by every replay)
+        if (start >= 0 && higher && !ev && a != e_end) atomicOr(err, ERR_INTERNAL);   // (a sync point is visited by every replay)
         const int exit_a = a;
         int lm = last_mend;
 #pragma unroll
@@ -546,24 +559,12 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
         const int lm_before = __shfl_up_sync(0xFFFFFFFFu, lm, 1);
         const int sp_in = lane == 0 ? sp_w : max(sp_w, lm_before);
         const int lm_all = __shfl_sync(0xFFFFFFFFu, lm, 31);
-        // 4. the reference's tests per match, in lane order
-        uint32_t k_l = 0;
-        int ev = 0, ev_q = 0, ev_a = 0, ev_sp = 0;
+        // 4. the lane's first match, now that its searchPos is known (the end of the last match of the lanes before)
         if (n_l) {
-          int sp = sp_in;
-          a = start;
-          while (a < e_end) {
-            bool hit;
-            const int nx = step_at(a, e_end, &hit);
-            if (hit) {
-              const int q = index_of(sp, a);
-              if (full && q + S > defer_line) { ev = 1; break; }
-              if (q < a) { ev = 2; ev_q = q; ev_a = a; ev_sp = sp; break; }
-              k_l++;
-              sp = nx;
-            }
-            a = nx;
-          }
+          const int q = index_of(sp_in, m0);
+          if (full && q + S > defer_line) { ev = 1; k_l = 0; }
+          else if (q < m0) { ev = 2; ev_q = q; ev_a = m0; ev_sp = sp_in; k_l = 0; }
+          else k_l++;
         }
         const uint32_t evm = __ballot_sync(0xFFFFFFFFu, ev != 0);
         const int F = evm ? __ffs(evm) - 1 : 32;
@@ -577,22 +578,37 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
         if (MODE == 2 && w + vtotal + (reloc ? 1u : 0u) > wend) { if (lane == 0) atomicOr(err, ERR_SLAB); n += vtotal + 1; stop = true; break; }
         if (MODE != 0 && valid) {
           unsigned long long wi = w + vincl - valid;
-          int sp = sp_in;
-          uint32_t left = valid;
-          a = start;
-          while (left) {
-            bool hit;
-            const int nx = step_at(a, e_end, &hit);
-            if (hit) {
+          if (valid <= 4) {
+            // straight from the registers
+            int sp = sp_in;
+            for (uint32_t i = 0; i < valid; i++) {
+              const int ma = i == 0 ? m0 : i == 1 ? m1 : i == 2 ? m2 : m3;
               if (wi < wend) {
                 ReaderHit h;
-                h.search_abs = (long long)cstart + sp; h.d_true = (uint32_t)(a - sp); h.d_text = (uint32_t)(a - sp); h.chunk = k;
+                h.search_abs = (long long)cstart + sp; h.d_true = (uint32_t)(ma - sp); h.d_text = (uint32_t)(ma - sp); h.chunk = k;
                 hits[wi] = h;
               }
-              wi++; left--;
-              sp = nx;
+              wi++;
+              sp = ma + S;
             }
-            a = nx;
+          } else {
+            int sp = sp_in;
+            uint32_t left = valid;
+            a = start;
+            while (left) {
+              bool hit;
+              const int nx = step_at(a, e_end, &hit);
+              if (hit) {
+                if (wi < wend) {
+                  ReaderHit h;
+                  h.search_abs = (long long)cstart + sp; h.d_true = (uint32_t)(a - sp); h.d_text = (uint32_t)(a - sp); h.chunk = k;
+                  hits[wi] = h;
+                }
+                wi++; left--;
+                sp = nx;
+              }
+              a = nx;
+            }
           }
         }
         w += vtotal; n += vtotal;
@@ -857,6 +873,11 @@ __device__ __forceinline__ void reader_record(const DevMeta& m, const uint32_t* 
       if (mtags[2 * g] >= 0) { rec[2 * g] = mtags[2 * g]; rec[2 * g + 1] = mtags[2 * g + 1]; }
       else { rec[2 * g] = -1; rec[2 * g + 1] = -1; }
     }
+    return;
+  }
+  if (m.sl_n > 0 && m.sl_caps_ok) {
+    // straight-line program: every group is set, at a fixed distance from the match start
+    for (int g = 0; g < nc; g++) rec[g] = start + (int64_t)m.sl_cap[g];
     return;
   }
   int32_t caps[MAX_CAPS];
