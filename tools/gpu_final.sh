@@ -18,7 +18,7 @@ except Exception as ex:
 PY
 done
 for w in c3 c2 c4 c5; do
-  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$w.csv \
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"findall|rgx|match_multi|find_reader|replace_batch|exclusive_scan|max_len" -c 400 --csv --log-file $out/launches_$w.csv \
      python bench.py --workload $w --steps 2 --warmup 3 --no-e2e --no-cpu --no-parity > $out/ncu_$w.log 2>&1
 done
 cap() {  # name workload kernel-regex extra-args
