@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
           cu = __shfl_sync(0xFFFFFFFFu, exit_a, last);
           cover = max(cover, __shfl_sync(0xFFFFFFFFu, incl, 31));
           P += RT_TILE;
+          __syncwarp();                    // (the tests above read Mprev)
           Mprev[lane] = U[32 + lane];
           prev_ok = true;
         } else if (!reloc) {

@@ -130,12 +130,11 @@ def settle_pre_halo_chain(run_pre, run_from, rank, world, shard_start, all_gathe
     while True:
         rounds += 1
         pairs = all_gather_pair((entry, exit_cur))
-        want = [0] + [int(pairs[r - 1][1]) for r in range(1, world)]
-        bad = [r for r in range(world) if int(pairs[r][0]) != want[r]]
+        bad = pre_halo_bad_ranks(pairs, world)
         if not bad:
             return entry, exit_cur, payload, rounds
         if rank in bad:
-            entry = want[rank]
+            entry = int(pairs[rank - 1][1])
             exit_cur, payload = run_from(entry)
         if rounds > world + 1:
             raise RuntimeError("cursor exchange did not converge")
@@ -160,6 +159,52 @@ def torch_all_gather_pair(group=None, device=None):
             flat = [int(v) for t in out for v in t.tolist()]
         return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
     return fn
+
+
+def torch_all_gather_pair_async(group=None, device=None):
+    """The same collective, split in two: post(pair) enqueues the all-gather of this rank's two int64 and returns a
+    handle; collect(handle) waits for it and returns every rank's pair.  A caller that runs the same sharded step over
+    and over posts the confirmation of step k and collects it while step k + 1 computes (bench.py): the collective's
+    latency and the ranks' skew stay off the critical path.  Two buffer sets alternate, so at most one handle may be
+    outstanding when the next is posted."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    on_gpu = device is not None and str(device).startswith("cuda")
+    sets = []
+    for _ in range(2):
+        pin = torch.zeros(2, dtype=torch.int64)
+        if on_gpu:
+            pin = pin.pin_memory()
+        sets.append((pin, torch.zeros(2, dtype=torch.int64, device=device), torch.zeros(2 * world, dtype=torch.int64, device=device)))
+    state = {"k": 0}
+
+    def post(pair):
+        pin, src, dst = sets[state["k"] & 1]
+        state["k"] += 1
+        pin[0] = int(pair[0])
+        pin[1] = int(pair[1])
+        src.copy_(pin, non_blocking=True)
+        if on_gpu and hasattr(dist, "all_gather_into_tensor"):
+            work = dist.all_gather_into_tensor(dst, src, group=group, async_op=True)
+            return (work, dst, None)
+        out = [torch.zeros_like(src) for _ in range(world)]
+        work = dist.all_gather(out, src, group=group, async_op=True)
+        return (work, None, out)
+
+    def collect(handle):
+        work, dst, out = handle
+        work.wait()
+        flat = dst.tolist() if dst is not None else [int(v) for t in out for v in t.tolist()]
+        return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
+    return post, collect
+
+
+def pre_halo_bad_ranks(pairs, world):
+    """The confirmation rule of settle_pre_halo_chain on gathered (entry, exit) pairs: rank r's carried entry cursor must
+    equal rank r - 1's exit cursor (rank 0 enters at 0).  Returns the list of ranks whose entry is wrong."""
+    want = [0] + [int(pairs[r - 1][1]) for r in range(1, world)]
+    return [r for r in range(world) if int(pairs[r][0]) != want[r]]
 
 
 def torch_all_gather_i64(group=None, device=None):

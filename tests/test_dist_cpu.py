@@ -208,3 +208,44 @@ def test_pre_halo_cursor_confirmation_gloo(world, pre):
         assert res[r][1] == res[r - 1][2]          # every entry is the predecessor's exit
     if pre >= total_len:
         assert all(r[5] == 0 for r in res) and all(r[4] == 1 for r in res)   # confirmed at once: no redo, one round
+
+
+def _worker_async_pairs(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        post, collect = rd.torch_all_gather_pair_async()
+        # the confirmation of step k is posted after step k and collected during step k + 1 (bench.py's sharded FindAll)
+        seen = []
+        pending = None
+        for step in range(5):
+            pair = (0 if rank == 0 else 1000 * rank + step, 1000 * (rank + 1) + step)      # entry == predecessor's exit
+            if step == 3 and rank == 1:
+                pair = (7, pair[1])                                                           # rank 1 carries a wrong cursor once
+            h = post(pair)
+            if pending is not None:
+                seen.append(rd.pre_halo_bad_ranks(collect(pending), world))
+            pending = h
+        seen.append(rd.pre_halo_bad_ranks(collect(pending), world))
+        q.put((rank, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_deferred_cursor_confirmation_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_async_pairs, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # every rank sees the same verdict per step: all fine except step 3, where rank 1's entry is wrong
+    assert got[0] == got[1] == [[], [], [], [1], []]
+    assert rd.pre_halo_bad_ranks([(0, 10), (10, 20), (21, 30)], 3) == [2]
+    assert rd.pre_halo_bad_ranks([(5, 10), (10, 20)], 2) == [0]

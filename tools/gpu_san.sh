@@ -1,10 +1,10 @@
 #!/bin/bash
-# compute-sanitizer over smoke() (memcheck, then racecheck on the FindAll part), and the fuzz tests
+# compute-sanitizer over smoke() (memcheck), racecheck over the FindAll, FindReader (tile chase: table-driven and
+# table-free) and Replace kernels on small inputs
 out=gpurun_out/${1:-san}
 mkdir -p $out
-timeout 1200 python -m pytest tests/test_gpu_fuzz.py -m gpu -x -q > $out/fuzz.log 2>&1; echo "fuzz rc=$?" >> $out/fuzz.log; tail -5 $out/fuzz.log
 timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $out/memcheck.log 2>&1; echo "memcheck rc=$?" >> $out/memcheck.log
-tail -6 $out/memcheck.log
+tail -4 $out/memcheck.log
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "
 import regengo_b200 as rg
 from regengo_b200 import synth
@@ -12,5 +12,12 @@ p = rg.Pattern(synth.URL_PATTERN)
 print(p.find_all_offsets(synth.make_buffer('url', 600000))[0])
 p2 = rg.Pattern(synth.EMAIL_PATTERN)
 print(p2.find_all_offsets(synth.make_buffer('log', 300000))[0])
+s = synth.make_buffer('stream', 300000, digit_noise=0.05)
+print(rg.Pattern(synth.DATE_CAPTURE_PATTERN).find_reader_offsets(s, rg.StreamConfig(0, 0))[0])
+print(rg.Pattern(r'(?P<y>\d{4})-(?P<m>\d+)').find_reader_offsets(s, rg.StreamConfig(0, 0))[0])
+print(p.find_reader_offsets(synth.make_buffer('url', 300000), rg.StreamConfig(0, 0))[0])
+print(len(p2.replace_all(bytes(synth.make_buffer('log', 100000)), '[\$user]')))
 " > $out/racecheck.log 2>&1; echo "racecheck rc=$?" >> $out/racecheck.log
-tail -6 $out/racecheck.log
+tail -9 $out/racecheck.log
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_stream.py tests/test_gpu_replace.py -m gpu -x -q -k "not large_batch and not patterned_stream" > $out/memcheck_stream_replace.log 2>&1; echo "memcheck2 rc=$?" >> $out/memcheck_stream_replace.log
+tail -5 $out/memcheck_stream_replace.log
