@@ -94,3 +94,25 @@ def test_fuzz_find_reader(pattern, chunk):
         return
     n, so, ci, recs = p.find_reader_offsets(data)
     assert n == en and np.array_equal(so, eso) and np.array_equal(ci, eci) and np.array_equal(recs, erecs), pattern
+
+
+TEMPLATE = st.lists(st.sampled_from(["$0", "$1", "$2", "$g", "${g}", "${1}", "$$", "$", "<", ">", "x", " ", "$9", "$nobody", "\xe9"]),
+                    min_size=0, max_size=5).map("".join)
+
+
+@settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(PATTERN, TEMPLATE, st.lists(INPUT, min_size=1, max_size=6))
+def test_fuzz_replace_all(pattern, template, inputs):
+    """ReplaceAllBytesAppend: empty matches, anchors re-applied to every slice, relocated match text, unset groups."""
+    try:
+        p = rg.Pattern(pattern)
+    except rg.RegengoError:
+        return
+    if runs_forever_in_the_reference(p) or p.num_cap > 32 or p.info.find_memo:
+        return
+    o = Oracle(p.blob())
+    inputs = inputs + [b" ".join(inputs) * 3]
+    data, offs = rg.pack_inputs(inputs)
+    exp, eoffs = o.replace_batch(data, offs, template)
+    got, goffs = p.replace_all_batch(data, template, offsets=offs)
+    assert np.array_equal(goffs, eoffs) and np.array_equal(got, exp), (pattern, template)
