@@ -373,7 +373,7 @@ class FindAllWork:
         self.total_matches = 0
         plan = self.pat.device_plan()
         self.kernel = ("findall_scan6_kernel" if plan.get("fast_tdfa_scan") else "findall_scan_btrun_kernel" if plan.get("run_anchor")
-                       else "findall_scan_kernel")
+                       else "findall_scan_linear_kernel" if plan.get("linear_findall_scan") else "findall_scan_kernel")
         self.algorithmic_bytes = self.n_bytes
 
     def step(self):

@@ -22,6 +22,7 @@
 #include "kernels_btrun.cuh"
 #include "kernels_stream.cuh"
 #include "kernels_replace.cuh"
+#include "kernels_scanlin.cuh"
 #include "replace_template.hpp"
 
 using namespace rgx;
@@ -596,6 +597,7 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   kv("run_literal", m.run_ok ? m.run_lit : -1);
   kv("run_linear_elements", m.lin_n);
   kv("straight_line_steps", m.sl_n);
+  kv("linear_findall_scan", (!fast_tdfa_scan_ok(m) && !(m.find_engine == FIND_BT && m.run_ok) && m.find_engine == FIND_BT && m.sl_n > 0 && m.sl_n <= 32 && m.sl_caps_ok) ? 1 : 0);
   kv("straight_line_classes", m.sl_ncls);
   kv("n_alt", m.n_alt);
   kv("n_empty", m.n_empty);

@@ -424,3 +424,52 @@ def test_fast_scan_first_byte_set_filter():
             arr[:len(t)] = t
             arr[len(arr) - len(t):] = t
             check_find_all(p, o, bytes(arr))
+
+
+def test_find_all_straight_line_scan():
+    """Straight-line backtracking programs (no Alt, one ASCII class per step) take findall_scan_linear_kernel: the records
+    of a segment are the bits of a bit-parallel plane.  Lengths 1, 10 and 32; matches across unit (64 B), iteration
+    (2 KiB) and segment (8 KiB) boundaries, at both buffer ends, overlapping candidates (the cursor keeps the leftmost),
+    all-digit input (every start is a record: the slabs grow), bytes >= 128, odd buffer lengths, device pointers at
+    every 16-byte misalignment."""
+    import torch
+    import ctypes as C
+    from regengo_b200 import _lib
+    rng = np.random.default_rng(29)
+    date = r"(?P<year>\d{4})-(?P<month>\d{2})-(?P<day>\d{2})"
+    for pat in (date, r"(\d)", r"(\d{32})", r"(?P<a>[a-f])(?P<b>\d\d)(x)"):
+        p, o = pair(pat)
+        assert p.device_plan()["linear_findall_scan"] == 1, pat
+        S = p.device_plan()["straight_line_steps"]
+        sample = {10: b"2024-01-15", 1: b"7", 32: b"12345678901234567890123456789012", 4: b"c42x"}[S]
+        buf = bytearray(rng.choice(np.frombuffer(b"abcxyz -\n\xc3\xa9", dtype=np.uint8), size=5 * 8192 + 333).tobytes())
+        for edge in (64, 2048, 8192, 16384, 3 * 8192):
+            for d in range(-S, 2, max(1, S // 3)):
+                buf[edge + d: edge + d + S] = sample
+        buf[:S] = sample
+        buf[len(buf) - S:] = sample
+        buf[700:700 + 3 * S] = sample * 3                  # adjacent
+        buf[900:900 + S - 1] = sample[:S - 1]              # cut short
+        check_find_all(p, o, bytes(buf))
+        check_find_all(p, o, bytes(buf[:8192 + S - 1]))    # the last match ends one byte past the buffer
+        check_find_all(p, o, bytes(buf), 7)                # n limit
+        check_find_all(p, o, sample)
+        check_find_all(p, o, sample[:-1])
+        check_find_all(p, o, b"5" * 40000 if S != 4 else b"c42x" * 10000)
+        # device pointers at every misalignment of the 16-byte loads
+        data = np.frombuffer(bytes(buf), dtype=np.uint8)
+        d_all = torch.from_numpy(np.concatenate([np.zeros(32, np.uint8), data])).cuda()
+        nc = p.num_cap
+        cap = data.size + 16
+        d_out = torch.empty(cap * nc, dtype=torch.int64, device="cuda")
+        d_reps = torch.empty(cap, dtype=torch.int32, device="cuda")
+        n_rec = C.c_uint64()
+        for mis in (1, 5, 8, 15):
+            sub = data[mis:]
+            ecnt, erecs = o.find_all(sub)
+            r = _lib.load().rgx_find_all_dev(rg.context(0), p._h, d_all.data_ptr() + 32 + mis, sub.size, -1, d_out.data_ptr(), d_reps.data_ptr(),
+                                             cap, C.byref(n_rec))
+            _lib.check(r)
+            assert r == ecnt and n_rec.value == ecnt
+            assert np.array_equal(d_out[: ecnt * nc].cpu().numpy().reshape(ecnt, nc), erecs), (pat, mis)
+            assert bool((d_reps[:ecnt] == 1).all())
