@@ -597,6 +597,8 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   kv("run_literal", m.run_ok ? m.run_lit : -1);
   kv("run_linear_elements", m.lin_n);
   kv("straight_line_steps", m.sl_n);
+  kv("straight_line_prefix_steps", m.slp_n);
+  kv("linear_prefix_findall_scan", (!fast_tdfa_scan_ok(m) && !(m.find_engine == FIND_BT && m.run_ok) && m.find_engine == FIND_BT && m.sl_n == 0 && m.slp_n >= 2 && m.slp_n <= 32) ? 1 : 0);
   kv("linear_findall_scan", (!fast_tdfa_scan_ok(m) && !(m.find_engine == FIND_BT && m.run_ok) && m.find_engine == FIND_BT && m.sl_n > 0 && m.sl_n <= 32 && m.sl_caps_ok) ? 1 : 0);
   kv("straight_line_classes", m.sl_ncls);
   kv("n_alt", m.n_alt);

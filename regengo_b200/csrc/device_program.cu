@@ -330,8 +330,10 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
     if ((P.class_bits[(size_t)L * 8 + (b >> 5)] >> (b & 31)) & 1u) continue;
     w[m.off_inst + 4 * i] |= (uint32_t)IF_ATOMIC_LOOP << 8;
   }
-  // Straight-line whole program?  (captures and nops between single-byte steps, then Match)
-  if (P.find_engine == FIND_BT && m.n_alt == 0 && m.n_empty == 0) {
+  // Straight-line program, or at least a straight-line PREFIX: captures and nops between single-byte ASCII class steps
+  // from the start instruction on -- every match has to pass them in this order.  sl_n > 0: the whole program is such a
+  // line (then Match); slp_n: the steps before the first instruction that is not (an Alt, an EmptyWidth, Match, ...).
+  if (P.find_engine == FIND_BT) {
     std::vector<Bits256> classes;
     std::vector<uint8_t> steps;
     std::vector<int> cap_at(MAX_CAPS, -1);   // capture slot -> bytes consumed before its Capture instruction
@@ -361,21 +363,26 @@ void pack_program(const Program& P, std::vector<uint32_t>& w, DevMeta& m) {
       if (ok && consumes) {
         size_t k = 0;
         for (; k < classes.size(); k++) if (std::memcmp(classes[k].w, set.w, sizeof(set.w)) == 0) break;
+        if (k == classes.size() && classes.size() == 8) { ok = false; break; }
+        if (steps.size() >= 32) { ok = false; break; }
         if (k == classes.size()) classes.push_back(set);
-        if (classes.size() > 8 || steps.size() >= 32) { ok = false; break; }
         steps.push_back((uint8_t)k);
         pc = (int)in.out;
       }
     }
-    if (ok && done && !steps.empty()) {
-      m.sl_n = (int32_t)steps.size();
+    const bool whole = ok && done && !steps.empty() && m.n_alt == 0 && m.n_empty == 0;
+    if (whole || steps.size() >= 2) {
+      m.slp_n = (int32_t)steps.size();
+      m.sl_n = whole ? (int32_t)steps.size() : 0;
       m.sl_ncls = (int32_t)classes.size();
       for (size_t i = 0; i < steps.size(); i++) m.sl_cls[i] = steps[i];
-      // every capture of a straight-line program sits at a fixed distance from the match start (slots 0 / 1: the match)
-      m.sl_caps_ok = prog.num_cap <= MAX_CAPS ? 1 : 0;
-      for (int slot = 0; slot < prog.num_cap && slot < MAX_CAPS; slot++) {
-        const int at = slot == 0 ? 0 : slot == 1 ? (int)steps.size() : cap_at[slot];
-        if (at < 0) m.sl_caps_ok = 0; else m.sl_cap[slot] = (uint8_t)at;
+      if (whole) {
+        // every capture of a straight-line program sits at a fixed distance from the match start (slots 0 / 1: the match)
+        m.sl_caps_ok = prog.num_cap <= MAX_CAPS ? 1 : 0;
+        for (int slot = 0; slot < prog.num_cap && slot < MAX_CAPS; slot++) {
+          const int at = slot == 0 ? 0 : slot == 1 ? (int)steps.size() : cap_at[slot];
+          if (at < 0) m.sl_caps_ok = 0; else m.sl_cap[slot] = (uint8_t)at;
+        }
       }
       m.off_sl_cm = (uint32_t)w.size();
       for (uint32_t c0 = 0; c0 < 256; c0 += 4) {

@@ -89,6 +89,7 @@ struct DevMeta {
   uint8_t sl_cls[32];
   uint8_t sl_cap[32];          // capture slot -> offset from the match start (valid when sl_caps_ok)
   int32_t sl_caps_ok;
+  int32_t slp_n;               // straight-line PREFIX: steps every match passes first (== sl_n for a whole line; < 2: none)
 };
 
 struct DeviceImage {

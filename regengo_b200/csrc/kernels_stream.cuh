@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(256) find_reader_table_kernel(const DevMeta m,
 // that do not exist = 0xFF): cand = positions whose byte passes step 0, alive = positions that pass all S steps (the
 // matches, length S), pl[0..5] = the number of steps survived, bit-sliced (an attempt that survives cnt < S steps
 // fails at offset cnt: the next attempt starts cnt + 1 further, and it looked at cnt + 1 bytes).
-__device__ __forceinline__ void linear_unit_planes(const DevMeta& m, const uint8_t* cm, uint32_t* bw, unsigned long long& cand,
+__device__ __forceinline__ void linear_unit_planes(const DevMeta& m, const int S, const uint8_t* cm, uint32_t* bw, unsigned long long& cand,
                                                    unsigned long long& alive, unsigned long long* pl) {
-  const int S = m.sl_n, ncls = m.sl_ncls;
+  const int ncls = m.sl_ncls;   // (S = m.sl_n for a whole straight-line program, m.slp_n for a straight-line prefix)
 #pragma unroll
   for (int q = 0; q < 24; q++) {
     const uint32_t x = bw[q];
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(128) find_reader_chase_kernel(const DevMeta m,
             }
           }
           unsigned long long cand, alive, pl[6];
-          linear_unit_planes(m, cm, bw, cand, alive, pl);
+          linear_unit_planes(m, S, cm, bw, cand, alive, pl);
           if (ub >= tile_end) { cand = 0; alive = 0; }
           __syncwarp();
           U[lane] = cand; U[32 + lane] = alive;

@@ -473,3 +473,40 @@ def test_find_all_straight_line_scan():
             assert r == ecnt and n_rec.value == ecnt
             assert np.array_equal(d_out[: ecnt * nc].cpu().numpy().reshape(ecnt, nc), erecs), (pat, mis)
             assert bool((d_reps[:ecnt] == 1).all())
+
+
+def test_find_all_straight_line_prefix_filter():
+    """Backtracking programs that START with a straight line of >= 2 single-byte steps (then an Alt, a loop, an
+    EmptyWidth ...): the bit plane of those steps is the candidate filter of findall_scan_linear_kernel<false> and the
+    goto-machine confirms its set bits.  Candidates that pass the prefix but fail later, matches longer than a unit and
+    a segment, prefixes cut by the buffer end, dense candidates."""
+    log = (r"(?P<timestamp>\d{4}-\d{2}-\d{2}T\d{2}:\d{2}:\d{2})(?:\.(?P<ms>\d{3}))?(?P<tz>Z|[+-]\d{2}:\d{2})?\s+\[(?P<level>\w+)\]\s+(?P<message>.+)")
+    cases = [
+        (log, [b"2024-01-15T10:30:00Z [INFO] started ok", b"2024-01-15T10:30:00.123+02:00 [ERROR] failed: x", b"2024-01-15T10:30:00 nope",
+               b"2024-01-15T10:30:0", b"1999-12-31T23:59:59   [W] " + b"m" * 9000]),
+        (r"(?P<g1>(?P<g2>b{2})+)(?P<g3>c+)", [b"bbc", b"bbbbbbcc", b"bbbc", b"bb", b"bbbbx", b"bb" * 5000 + b"c"]),
+        (r"(?P<k>ab)(?P<v>\d+|x)", [b"ab1", b"abx", b"ab", b"aab12", b"abab7"]),
+    ]
+    rng = np.random.default_rng(31)
+    for pat, toks in cases:
+        p, o = pair(pat)
+        d = p.device_plan()
+        assert d["linear_prefix_findall_scan"] == 1 and d["straight_line_prefix_steps"] >= 2, pat
+        filler = [b"lorem", b"2024-01", b"ab", b"bb", b"b", b"-", b"T", b"\n", b" ", b"caf\xc3\xa9", b"12:30"]
+        parts = []
+        for _ in range(30000):
+            parts.append(toks[int(rng.integers(0, len(toks)))] if rng.integers(0, 9) == 0 else filler[int(rng.integers(0, len(filler)))])
+            parts.append(b"\n" if rng.integers(0, 4) == 0 else b" ")
+        buf = b"".join(parts)
+        assert check_find_all(p, o, buf) > 100
+        check_find_all(p, o, buf[3:200003])
+        check_find_all(p, o, buf, 11)
+        for t in toks:
+            check_find_all(p, o, t)
+            arr = bytearray(b"." * (3 * 8192 + 50))
+            for edge in (64, 2048, 8192, 16384):
+                for dlt in (-len(t), -len(t) // 2, -1, 0):
+                    if edge + dlt >= 0 and len(t) < 4000:
+                        arr[edge + dlt: edge + dlt + len(t)] = t
+            arr[len(arr) - min(len(t), 40):] = t[:min(len(t), 40)]
+            check_find_all(p, o, bytes(arr))

@@ -84,7 +84,7 @@ def main():
             continue
         p = rg.Pattern(pat)
         plan = p.device_plan()
-        kernel = ("findall_scan6_kernel" if plan.get("fast_tdfa_scan") else "findall_scan_btrun_kernel" if plan.get("run_anchor") else "findall_scan_linear_kernel" if plan.get("linear_findall_scan") else "findall_scan_kernel")
+        kernel = ("findall_scan6_kernel" if plan.get("fast_tdfa_scan") else "findall_scan_btrun_kernel" if plan.get("run_anchor") else "findall_scan_linear_kernel" if plan.get("linear_findall_scan") else "findall_scan_linear_kernel<prefix filter>" if plan.get("linear_prefix_findall_scan") else "findall_scan_kernel")
         host = make_block(tokens, block, seed=zlib.crc32(name.encode()) & 0xFFFF)
         d_block = torch.from_numpy(host.copy()).to(dev)
         buf = d_block.repeat((n_bytes + block - 1) // block)[:n_bytes].contiguous()
