@@ -601,6 +601,16 @@ int64_t rgx_program_device_plan(const rgx_program* p, char* buf, size_t cap) {
   kv("linear_prefix_findall_scan", (!fast_tdfa_scan_ok(m) && !(m.find_engine == FIND_BT && m.run_ok) && m.find_engine == FIND_BT && m.sl_n == 0 && m.slp_n >= 2 && m.slp_n <= 32) ? 1 : 0);
   kv("linear_findall_scan", (!fast_tdfa_scan_ok(m) && !(m.find_engine == FIND_BT && m.run_ok) && m.find_engine == FIND_BT && m.sl_n > 0 && m.sl_n <= 32 && m.sl_caps_ok) ? 1 : 0);
   kv("straight_line_classes", m.sl_ncls);
+  kv("sl_cm_off", m.off_sl_cm);
+  kv("sl_caps_ok", m.sl_caps_ok);
+  {
+    // class index of every step, capture offsets (hex, one byte each): what the bit-plane kernels read
+    s += ", \"sl_cls\": \"";
+    for (int i = 0; i < m.slp_n && i < 32; i++) { char h[8]; std::snprintf(h, sizeof h, "%02x", m.sl_cls[i]); s += h; }
+    s += "\", \"sl_cap\": \"";
+    for (int i = 0; i < m.num_cap && i < 32 && m.sl_caps_ok; i++) { char h[8]; std::snprintf(h, sizeof h, "%02x", m.sl_cap[i]); s += h; }
+    s += "\"";
+  }
   kv("n_alt", m.n_alt);
   kv("n_empty", m.n_empty);
   s += ", \"prefix\": \"";
