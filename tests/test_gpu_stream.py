@@ -181,3 +181,41 @@ def test_tile_chase_events_engines_and_alignment():
         b2[end - 10:end] = b"2024-07-04"
         b2[2048 - 5:2048 + 5] = b"2024-08-05"
         check_reader(pl, ol, bytes(b2))
+
+
+def test_runs_of_chunks_host_pieces_and_device_runs(monkeypatch):
+    """Long streams are searched in runs of whole chunks: the host path uploads / searches / downloads them as pieces on
+    three streams, the device path bounds the per-chunk hit regions.  RGX_READER_MIN_RUN (a test knob) forces runs of
+    1, 3 and 7 chunks on a stream of 40 chunks -- including the flush pass of an exactly filled last buffer -- and the
+    records must come out in chunk order, identical to the oracle's."""
+    import ctypes as C
+    import torch
+    from regengo_b200 import _lib
+    L = _lib.load()
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    pu, ou = pair(synth.URL_PATTERN)
+    B, Lo = o.stream_config(0, 0)
+    date_stream = synth.make_buffer("stream", 40 * (B - Lo) + 1234, digit_noise=0.02)
+    exact = bytes(date_stream[: B + 5 * (B - Lo)])                 # the last read fills the buffer exactly: flush pass
+    url_stream = synth.make_buffer("url", 12 * 65536 + 999)
+    for run in ("1", "3", "7"):
+        monkeypatch.setenv("RGX_READER_MIN_RUN", run)
+        check_reader(p, o, date_stream)
+        check_reader(p, o, exact)
+        check_reader(pu, ou, url_stream)
+        # device pointers: rgx_find_reader_dev over the whole stream and over a chunk range
+        data = np.frombuffer(bytes(date_stream), dtype=np.uint8)
+        en, eso, eci, erecs = o.find_reader(data)
+        d = torch.from_numpy(data.copy()).cuda()
+        nc = p.num_cap
+        so = torch.empty(en + 8, dtype=torch.int64, device="cuda")
+        ci = torch.empty(en + 8, dtype=torch.int32, device="cuda")
+        rec = torch.empty((en + 8) * nc, dtype=torch.int64, device="cuda")
+        n = L.rgx_find_reader_dev(rg.context(0), p._h, d.data_ptr(), 0, data.size, data.size, 0, 0, 0, -1, so.data_ptr(), ci.data_ptr(), rec.data_ptr(), en + 8)
+        _lib.check(n)
+        assert n == en and np.array_equal(so[:en].cpu().numpy(), eso) and np.array_equal(ci[:en].cpu().numpy(), eci)
+        assert np.array_equal(rec[: en * nc].cpu().numpy().reshape(en, nc), erecs)
+        n2 = L.rgx_find_reader_dev(rg.context(0), p._h, d.data_ptr(), 0, data.size, data.size, 0, 0, 5, 11, so.data_ptr(), ci.data_ptr(), rec.data_ptr(), en + 8)
+        _lib.check(n2)
+        sel = (eci >= 5) & (eci < 16)
+        assert n2 == int(sel.sum()) and np.array_equal(so[:n2].cpu().numpy(), eso[sel]) and np.array_equal(ci[:n2].cpu().numpy(), eci[sel])
