@@ -308,8 +308,20 @@ class Pattern:
         return None
 
     def find_reader_count(self, reader, cfg=None):
+        """FindReaderCount(r, cfg) (int64, error): the number of matches (streaming.go:258-283)."""
         data = reader.read() if hasattr(reader, "read") else bytes(reader)
         return self.find_reader_offsets(data, cfg)[0]
+
+    def find_reader_first(self, reader, cfg=None):
+        """FindReaderFirst(r, cfg) (*TBytesResult, int64, error): the first match and its StreamOffset, or (None, 0)
+        (streaming.go:285-313: FindReader with a callback that copies the result and returns false)."""
+        data = reader.read() if hasattr(reader, "read") else bytes(reader)
+        if isinstance(data, str):
+            data = data.encode("utf-8")
+        n, so, _, recs = self.find_reader_offsets(data, cfg)
+        if n == 0:
+            return None, 0
+        return Result(data, recs[0], self.group_names), int(so[0])
 
 
 def compile(pattern, **kw):  # noqa: A001  (mirrors regengo.Compile)

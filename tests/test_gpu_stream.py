@@ -219,3 +219,17 @@ def test_runs_of_chunks_host_pieces_and_device_runs(monkeypatch):
         _lib.check(n2)
         sel = (eci >= 5) & (eci < 16)
         assert n2 == int(sel.sum()) and np.array_equal(so[:n2].cpu().numpy(), eso[sel]) and np.array_equal(ci[:n2].cpu().numpy(), eci[sel])
+
+
+def test_find_reader_first_and_count():
+    # streaming_test.go:143-162 (early termination), FindReaderCount / FindReaderFirst (streaming.go:258-313)
+    import io
+    p, o = pair(synth.DATE_CAPTURE_PATTERN)
+    data = b"".join(b"entry %d on 2024-%02d-15; " % (i, 1 + i % 12) for i in range(100))
+    assert p.find_reader_count(io.BytesIO(data)) == 100
+    first, off = p.find_reader_first(io.BytesIO(data))
+    assert first.match == b"2024-01-15" and off == data.index(b"2024-01-15")
+    assert p.find_reader_first(io.BytesIO(b"x" * 10000)) == (None, 0)
+    seen = []
+    p.find_reader(io.BytesIO(data), rg.StreamConfig(), lambda m: (seen.append(m.stream_offset), len(seen) < 5)[1])
+    assert len(seen) == 5
